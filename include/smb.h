@@ -1,0 +1,145 @@
+/*
+ * smb.h -- C ABI of the B200 (sm_100a) SIFT descriptor matcher ("sift match, B200").
+ *
+ * Drop-in boundary for ONE call of the reference (garyjyzhang/scanner-colmap):
+ *
+ *     colmap::MatchSiftFeaturesCPU(sift_options_, descriptors1, descriptors2, &featureMatches);
+ *         -- integration/op_cpp/sequential_matching.cc:154
+ *
+ * as it is driven by the per-row pair loop of the SequentialMatchingCPU Scanner
+ * op (sequential_matching.cc:139-181).  The op shim (scanner_colmap_b200/op/)
+ * and the Python mirror (scanner_colmap_b200/matcher.py, ctypes) are the only
+ * callers.  Plain pointers and sizes only; no exceptions cross this boundary;
+ * no global state besides the create-time error string; one CUDA stream set per
+ * handle; a handle may be used by one thread at a time (Scanner calls execute()
+ * serially per kernel instance), different handles are independent.
+ *
+ * All functions returning int return SMB_OK (0) or a negative SMB_E* code;
+ * smb_last_error() gives the text.  The op shim CHECK_EQ's the code against 0,
+ * which matches the reference's abort-on-error convention (io.cc:392-404).
+ */
+#ifndef SMB_H_
+#define SMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB_ABI_VERSION 1
+#define SMB_DESC_DIM 128 /* SIFT descriptor bytes; FeatureDescriptors cols, io.cc:181-194 */
+
+enum {
+  SMB_OK = 0,
+  SMB_EINVAL = -1,    /* bad argument (null pointer, d != 128, unknown image id ...) */
+  SMB_ECUDA = -2,     /* CUDA runtime / driver error; text in smb_last_error */
+  SMB_ENOMEM = -3,    /* host or device allocation failed */
+  SMB_ENODEVICE = -4, /* no sm_100 device / wrong architecture: there is NO CPU fallback */
+  SMB_ECAPACITY = -5  /* caller buffer too small */
+};
+
+/* Which device kernel computes the dot-product tiles. */
+enum {
+  SMB_ENGINE_TCGEN05 = 0, /* production: TMA + tcgen05.mma kind::i8 + TMEM (default) */
+  SMB_ENGINE_DP4A = 1     /* test-only device cross-check: CUDA-core __dp4a tiles, same epilogue contract */
+};
+
+/* Mirrors the fields of colmap::SiftMatchingOptions that MatchSiftFeaturesCPU reads,
+ * filled by the op from siftFeatureMatchingArgs (sequential_matching.cc:40-55,
+ * defaults colmap.proto:14-24).  max_ratio / max_distance are the double options
+ * narrowed to float exactly where COLMAP narrows them (the FindBestMatches call). */
+typedef struct smb_options {
+  double max_ratio;       /* colmap.proto:14  default 0.8 */
+  double max_distance;    /* colmap.proto:17  default 0.7 */
+  int32_t cross_check;    /* colmap.proto:20  default true */
+  int32_t max_num_matches; /* colmap.proto:23 default 32768; accepted and, like the reference's CPU
+                              path, NOT applied (only COLMAP's GPU matcher truncates) */
+  int32_t engine;         /* SMB_ENGINE_* */
+  int32_t profile;        /* non-zero: record CUDA events per kernel, see smb_get_timing */
+} smb_options;
+
+/* == colmap::FeatureMatch {point2D_idx1, point2D_idx2}, the 8-byte POD that io.cc:267-289
+ * memcpy-serialises into the two_view_geometries row. */
+typedef struct smb_match {
+  uint32_t idx1;
+  uint32_t idx2;
+} smb_match;
+
+typedef struct smb_handle smb_handle;
+typedef struct smb_result smb_result;
+
+/* Device timings of the most recent smb_match_pairs call (milliseconds, CUDA events on the
+ * handle's stream; valid only when options.profile != 0). */
+typedef struct smb_timing {
+  float total_ms;       /* first upload to last device->host copy */
+  float score_ms;       /* the dot-product + filter kernel(s) only (summed over internal batches) */
+  float decide_ms;      /* top-2 resolve + tests + cross-check + compaction kernels */
+  uint32_t score_launches;
+  uint32_t total_launches; /* every kernel of this library launched by the call */
+  uint64_t candidates;  /* score-matrix entries that survived the integer pre-filter */
+  uint64_t ops;         /* 2 * sum(n1 * n2) * 128 over the call's pairs */
+} smb_timing;
+
+void smb_default_options(smb_options* opts);
+int smb_abi_version(void);
+
+/* Create a matcher bound to one CUDA device.  Fails with SMB_ENODEVICE when the device is not
+ * compute capability 10.x: there is no fallback path. */
+int smb_create(int cuda_device, const smb_options* opts, smb_handle** out);
+void smb_destroy(smb_handle* h);
+/* h may be NULL to read the error of a failed smb_create (thread-local). */
+const char* smb_last_error(const smb_handle* h);
+
+/* Replace the options (thresholds are re-derived; cached images stay). */
+int smb_set_options(smb_handle* h, const smb_options* opts);
+
+/* Descriptor cache.  Replaces the per-row re-deserialisation of
+ * read_matrix_from_element<FeatureDescriptors> (io.cc:181-194, call sites
+ * sequential_matching.cc:120-121): an image is uploaded once per handle and reused by
+ * every pair that names it.  desc = n x 128 uint8 row-major host memory (pageable or
+ * pinned); the call returns after the bytes have been consumed.  Re-putting an existing
+ * id replaces it. */
+int smb_put_image(smb_handle* h, uint32_t image_id, const uint8_t* desc, size_t n, size_t d);
+/* Batched form: all copies are queued, one wait at the end (the op uses it per stencil window). */
+int smb_put_images(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
+                   size_t count, size_t d);
+/* Same, from device memory of this or a peer device (halo exchange over NVLink). */
+int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d);
+int smb_has_image(const smb_handle* h, uint32_t image_id);
+int smb_evict_image(smb_handle* h, uint32_t image_id);
+int smb_clear_images(smb_handle* h);
+/* Device address and row count of a cached image (read-only; valid until eviction/put/destroy). */
+int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** dev_ptr, size_t* n);
+
+/* Match npairs (image_id1, image_id2) pairs of cached images: the flattened pair loop of
+ * sequential_matching.cc:139-181.  Result i holds exactly what MatchSiftFeaturesCPU would have
+ * written to featureMatches for pair i: (idx1, idx2) in ascending idx1. */
+int smb_match_pairs(smb_handle* h, const uint32_t* pairs /* [npairs][2] */, size_t npairs, smb_result** out);
+
+size_t smb_result_num_pairs(const smb_result* r);
+/* Matches of pair i; pointer is into pinned host memory owned by the result. */
+const smb_match* smb_result_matches(const smb_result* r, size_t i, size_t* count);
+size_t smb_result_total_matches(const smb_result* r);
+void smb_result_release(smb_handle* h, smb_result* r);
+
+/* One-shot form with the exact shape of the replaced call: host descriptors in, matches out.
+ * out must hold min(n1, n2) entries when cross_check, else n1.  Nothing is cached. */
+int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const uint8_t* desc2, size_t n2,
+                          smb_match* out, size_t capacity, size_t* count);
+
+int smb_get_timing(const smb_handle* h, smb_timing* t);
+
+/* Integer pre-filter derived from the options and the host libm acosf table: score entries
+ * below *min_score cannot change any accept/reject decision ("Filter"). */
+int smb_get_filter(const smb_handle* h, int32_t* min_score, int32_t* min_best);
+
+/* CUDA stream the handle launches on (cudaStream_t as void*), for external event timing. */
+void* smb_stream(const smb_handle* h);
+int smb_synchronize(smb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMB_H_ */

@@ -1,0 +1,388 @@
+// Device side of the matcher.  Three kernels per (sub-)batch of image pairs:
+//
+//   score_*      N1 x N2 exact u8*u8->s32 dot products per pair, never written to memory: each
+//                128 x 256 accumulator tile is scanned in place and only entries >= min_score (the
+//                integer pre-filter derived from the acos table, see smb.cu derive_filter) are fed to
+//   top2_insert  order-independent best / second-best accumulators per row AND per column
+//                (64-bit keys: score << 32 | ~index, so max == "highest score, lowest index":
+//                COLMAP's strict '>' ascending scan; the runner-up key's score is the second-best of
+//                the multiset).
+//   decide       per pair: acos-table distance test, ratio test ('>='), cross-check, ordered
+//                compaction into FeatureMatch {idx1, idx2} rows (ascending idx1).
+//
+// Reference semantics: COLMAP 3.5 feature/sift.cc ComputeSiftDistanceMatrix /
+// FindBestMatchesOneWay / FindBestMatches, called at
+// /root/reference/integration/op_cpp/sequential_matching.cc:154.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace smb {
+
+constexpr int kDim = 128;            // descriptor bytes == GEMM K
+constexpr int kStripRows = 128;      // rows of image 1 per work item == UMMA M
+constexpr int kTileCols = 256;       // columns (rows of image 2) per accumulator tile == UMMA N
+constexpr int kRowPad = 256;         // every cached image occupies a multiple of this many pool rows
+constexpr int kLutSize = 512 * 512 + 1;
+
+struct PairMeta {
+  uint32_t a_row0;   // pool row of image 1
+  uint32_t n1;
+  uint32_t b_row0;   // pool row of image 2
+  uint32_t n2;
+  uint64_t acc_off;  // accumulators: rows at [acc_off, acc_off+n1), columns at [acc_off+n1, acc_off+n1+n2)
+  uint32_t out_slot; // index into the per-call pair_out array
+  uint32_t pad_;
+};
+
+struct WorkItem {     // one 128-row strip of one pair against all of image 2
+  uint32_t a_row;     // pool row of the strip
+  uint32_t b_row;     // pool row of image 2
+  uint32_t n_btiles;  // number of 256-column tiles
+  uint32_t pair;      // index into PairMeta (batch-local)
+};
+
+struct TopTwo {
+  unsigned long long k1;  // best key
+  unsigned long long k2;  // runner-up key
+};
+
+struct PairOut {
+  uint32_t start;  // offset into the match buffer
+  uint32_t count;
+};
+
+__device__ __forceinline__ unsigned long long make_key(int score, uint32_t idx) {
+  return (static_cast<unsigned long long>(static_cast<uint32_t>(score)) << 32) | static_cast<uint32_t>(~idx);
+}
+
+// Insert into a {best, runner-up} pair with two atomic max operations.  Keys are distinct (the
+// index is part of the key), k1 ends as the global maximum, and every insertion hands
+// min(previous best, key) to k2, so k2 ends as the second-largest key regardless of order.
+__device__ __forceinline__ void top2_insert(TopTwo* t, unsigned long long key) {
+  unsigned long long old = atomicMax(&t->k1, key);
+  unsigned long long loser = old < key ? old : key;
+  if (loser) atomicMax(&t->k2, loser);
+}
+
+// A score that survived the pre-filter: feed the row- and column-direction accumulators.
+__device__ __noinline__ void emit_candidate(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc,
+                                            uint32_t pair, uint32_t a_row, uint32_t row_in_strip, uint32_t col,
+                                            int score, unsigned long long* cand_counter) {
+  const PairMeta pm = pairs[pair];
+  const uint32_t i = a_row - pm.a_row0 + row_in_strip;
+  if (i >= pm.n1 || col >= pm.n2) return;  // pool padding
+  TopTwo* rows = acc + pm.acc_off;
+  top2_insert(rows + i, make_key(score, col));
+  top2_insert(rows + pm.n1 + col, make_key(score, i));
+  if (cand_counter) atomicAdd(cand_counter, 1ull);
+}
+
+// =====================================================================================
+// Production score kernel: TMA -> swizzled smem -> tcgen05.mma kind::i8 -> TMEM -> filter
+// =====================================================================================
+constexpr int kStages = 4;                     // B-tile ring
+constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
+constexpr int kABytes = kStripRows * kDim;     // 16 KiB
+constexpr int kBBytes = kTileCols * kDim;      // 32 KiB
+constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter
+constexpr int kScoreThreads = 32 * (4 + kEpiWarps);
+constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + 256 /*barriers*/;
+
+struct ScoreBarriers {
+  uint64_t a_full[kAStages], a_empty[kAStages];
+  uint64_t b_full[kStages], b_empty[kStages];
+  uint64_t t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(ScoreBarriers) <= 256, "barrier block");
+
+template <int N>
+__device__ __forceinline__ int max_tree(const uint32_t (&v)[N]) {
+  // 3-input integer max (VIMNMX3): 0.5 ALU instruction per accumulator element
+  int m = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+#pragma unroll
+  for (int e = 3; e + 1 < N; e += 2) m = __vimax3_s32(m, (int)v[e], (int)v[e + 1]);
+  if ((N - 3) & 1) m = max(m, (int)v[N - 1]);
+  return m;
+}
+
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
+                     const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
+                     unsigned long long* cand_counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t smem_a = smem0;
+  const uint32_t smem_b = smem0 + kAStages * kABytes;
+  ScoreBarriers* bars =
+      reinterpret_cast<ScoreBarriers*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes + kStages * kBBytes);
+
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap);
+    for (int s = 0; s < kAStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->t_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->t_empty[s]), kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {  // whole warp: TMEM allocation (all 512 columns: two 256-column accumulators)
+    ptx::tmem_alloc_512(ptx::smem_u32(&bars->tmem_base));
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem w = items[it];
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[as]), aph ^ 1);
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bars->a_full[as]), kABytes);
+        ptx::tma_load_2d(smem_a + as * kABytes, &tmap, ptx::smem_u32(&bars->a_full[as]), 0, (int32_t)w.a_row);
+        if (++as == kAStages) { as = 0; aph ^= 1; }
+        for (uint32_t t = 0; t < w.n_btiles; ++t) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[bs]), bph ^ 1);
+          const uint32_t full = ptx::smem_u32(&bars->b_full[bs]);
+          ptx::mbar_arrive_expect_tx(full, kBBytes);
+          const int32_t r = (int32_t)(w.b_row + t * kTileCols);
+          ptx::tma_load_2d(smem_b + bs * kBBytes, &tmap, full, 0, r);
+          ptx::tma_load_2d(smem_b + bs * kBBytes + kBBytes / 2, &tmap, full, 0, r + kTileCols / 2);
+          if (++bs == kStages) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kStripRows, kTileCols);
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint32_t n_btiles = items[it].n_btiles;
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_full[as]), aph);
+        const uint64_t adesc = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
+        for (uint32_t t = 0; t < n_btiles; ++t) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->t_empty[ts]), tph ^ 1);
+          ptx::mbar_wait(ptx::smem_u32(&bars->b_full[bs]), bph);
+          ptx::tcgen05_fence_after();
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
+          const uint32_t d = tmem_base + ts * kTileCols;
+#pragma unroll
+          for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
+            ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+          ptx::umma_commit(ptx::smem_u32(&bars->b_empty[bs]));
+          ptx::umma_commit(ptx::smem_u32(&bars->t_full[ts]));
+          if (++bs == kStages) { bs = 0; bph ^= 1; }
+          if (++ts == 2) { ts = 0; tph ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&bars->a_empty[as]));
+        if (++as == kAStages) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ filter epilogue (8 warps)
+    const uint32_t quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are visible to this warp
+    const uint32_t half = (warp - 4) >> 2;        // which 128 of the tile's 256 columns
+    const uint32_t lane_addr = (quarter * 32u) << 16;
+    uint32_t ts = 0, tph = 0;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem w = items[it];
+      for (uint32_t t = 0; t < w.n_btiles; ++t) {
+        ptx::mbar_wait(ptx::smem_u32(&bars->t_full[ts]), tph);
+        ptx::tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
+        int m = 0;
+#pragma unroll
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c, v);
+          ptx::tmem_wait_ld();
+          m = max(m, max_tree(v));
+        }
+        if (__any_sync(0xffffffffu, m >= min_score)) {
+          // rare: re-read the half tile and hand every surviving entry to the accumulators
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c, v);
+            ptx::tmem_wait_ld();
+            if (m >= min_score) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if ((int)v[e] >= min_score)
+                  emit_candidate(pairs, acc, w.pair, w.a_row, quarter * 32 + lane,
+                                 t * kTileCols + half * 128 + c + e, (int)v[e], cand_counter);
+            }
+          }
+        }
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->t_empty[ts]));
+        if (++ts == 2) { ts = 0; tph ^= 1; }
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_512(tmem_base);
+  }
+}
+
+// =====================================================================================
+// Test-only device cross-check: the same contract on CUDA cores (__dp4a), no tensor cores,
+// no TMA.  Selected with SMB_ENGINE_DP4A; never the default.
+// =====================================================================================
+constexpr int kDp4aThreads = 256;
+constexpr int kDp4aCols = 64;
+
+__global__ void __launch_bounds__(kDp4aThreads)
+score_dp4a_kernel(const uint8_t* __restrict__ pool, const WorkItem* __restrict__ items, uint32_t n_items,
+                  const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
+                  unsigned long long* cand_counter) {
+  __shared__ uint32_t sa[kStripRows][kDim / 4 + 1];
+  __shared__ uint32_t sb[kDp4aCols][kDim / 4 + 1];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 8 rows x 4 columns each
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const WorkItem w = items[it];
+    const uint32_t* ga = reinterpret_cast<const uint32_t*>(pool + (size_t)w.a_row * kDim);
+    __syncthreads();
+    for (uint32_t x = tid; x < kStripRows * (kDim / 4); x += kDp4aThreads) sa[x >> 5][x & 31] = ga[x];
+    const uint32_t n_cols = w.n_btiles * kTileCols;
+    for (uint32_t c0 = 0; c0 < n_cols; c0 += kDp4aCols) {
+      const uint32_t* gb = reinterpret_cast<const uint32_t*>(pool + (size_t)(w.b_row + c0) * kDim);
+      __syncthreads();
+      for (uint32_t x = tid; x < kDp4aCols * (kDim / 4); x += kDp4aThreads) sb[x >> 5][x & 31] = gb[x];
+      __syncthreads();
+      uint32_t s[8][4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[r][c] = 0;
+      for (int k = 0; k < kDim / 4; ++k) {
+        uint32_t a[8], b[4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = sa[ty * 8 + r][k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = sb[tx * 4 + c][k];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) s[r][c] = __dp4a(a[r], b[c], s[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if ((int)s[r][c] >= min_score)
+            emit_candidate(pairs, acc, w.pair, w.a_row, ty * 8 + r, c0 + tx * 4 + c, (int)s[r][c], cand_counter);
+    }
+  }
+}
+
+// =====================================================================================
+// decide: FindBestMatchesOneWay tests + cross-check + ordered compaction, one CTA per pair
+// =====================================================================================
+constexpr int kDecideThreads = 512;
+
+// acosf(min(score / 512^2, 1)) through the host-libm table; rows/columns without any surviving
+// score (k1 == 0) never match.  Returns the matched index or -1.
+__device__ __forceinline__ int decide_one(const TopTwo t, const float* __restrict__ lut, float max_ratio,
+                                          float max_distance) {
+  const uint32_t best = static_cast<uint32_t>(t.k1 >> 32);
+  if (best == 0) return -1;
+  const uint32_t second = static_cast<uint32_t>(t.k2 >> 32);
+  const float bn = __ldg(lut + min(best, (uint32_t)(kLutSize - 1)));
+  if (bn > max_distance) return -1;
+  const float sn = __ldg(lut + min(second, (uint32_t)(kLutSize - 1)));
+  if (bn >= __fmul_rn(max_ratio, sn)) return -1;  // '>=' rejects best == second-best
+  return static_cast<int>(~static_cast<uint32_t>(t.k1));
+}
+
+__global__ void __launch_bounds__(kDecideThreads)
+decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, const float* __restrict__ lut,
+              float max_ratio, float max_distance, int cross_check, uint2* __restrict__ out /* FeatureMatch */,
+              unsigned long long* __restrict__ out_total, PairOut* __restrict__ pair_out) {
+  __shared__ uint32_t warp_sums[kDecideThreads / 32];
+  __shared__ uint32_t s_base;
+  const PairMeta pm = pairs[blockIdx.x];
+  TopTwo* rows = acc + pm.acc_off;
+  TopTwo* cols = rows + pm.n1;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  if (cross_check) {
+    for (uint32_t j = tid; j < pm.n2; j += kDecideThreads) {
+      const int m21 = decide_one(cols[j], lut, max_ratio, max_distance);
+      cols[j].k1 = static_cast<unsigned long long>(static_cast<uint32_t>(m21));
+    }
+  }
+  __syncthreads();
+
+  // pass 1: decide every row, remember the verdict in place, count
+  uint32_t cnt = 0;
+  for (uint32_t i = tid; i < pm.n1; i += kDecideThreads) {
+    int m12 = decide_one(rows[i], lut, max_ratio, max_distance);
+    if (m12 >= 0 && cross_check && static_cast<uint32_t>(cols[m12].k1) != i) m12 = -1;
+    rows[i].k1 = static_cast<unsigned long long>(static_cast<uint32_t>(m12));
+    cnt += (m12 >= 0);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) warp_sums[wid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t total = 0;
+    for (int w = 0; w < kDecideThreads / 32; ++w) total += warp_sums[w];
+    const unsigned long long base = atomicAdd(out_total, (unsigned long long)total);
+    s_base = static_cast<uint32_t>(base);
+    pair_out[pm.out_slot].start = static_cast<uint32_t>(base);
+    pair_out[pm.out_slot].count = total;
+  }
+  __syncthreads();
+  uint32_t running = s_base;
+
+  // pass 2: ordered write (ascending idx1), block-wide exclusive scan per chunk of rows
+  for (uint32_t i0 = 0; i0 < pm.n1; i0 += kDecideThreads) {
+    const uint32_t i = i0 + tid;
+    int m12 = -1;
+    if (i < pm.n1) m12 = static_cast<int>(static_cast<uint32_t>(rows[i].k1));
+    const uint32_t ballot = __ballot_sync(0xffffffffu, m12 >= 0);
+    __syncthreads();  // warp_sums reuse
+    if (lane == 0) warp_sums[wid] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = 0, chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < kDecideThreads / 32; ++w) {
+      const uint32_t s = warp_sums[w];
+      if (w < (int)wid) before += s;
+      chunk_total += s;
+    }
+    if (m12 >= 0) {
+      const uint32_t pos = running + before + __popc(ballot & ((1u << lane) - 1));
+      out[pos] = make_uint2(i, static_cast<uint32_t>(m12));
+    }
+    running += chunk_total;
+  }
+}
+
+}  // namespace smb

@@ -1,0 +1,788 @@
+// Host side of libsmb: the C ABI of include/smb.h.
+//
+// Replaces, for the Scanner op SequentialMatchingCPU, the call
+//   colmap::MatchSiftFeaturesCPU(...)      /root/reference/integration/op_cpp/sequential_matching.cc:154
+// and the per-row descriptor re-deserialisation feeding it
+//   read_matrix_from_element<FeatureDescriptors>   io.cc:181-194, sequential_matching.cc:120-121
+// with a per-handle descriptor pool in HBM and batched pair matching on one B200.
+//
+// There is deliberately no CPU path in this file: every entry point that computes needs an
+// sm_100 device and fails with SMB_ENODEVICE / SMB_ECUDA otherwise.
+#include "../../include/smb.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace {
+
+using namespace smb;
+
+thread_local std::string g_create_error;
+
+struct ImageEntry {
+  uint32_t row0;   // first pool row
+  uint32_t n;      // descriptor count
+  uint32_t rows;   // reserved pool rows (multiple of kRowPad)
+};
+
+struct Filter {
+  int32_t min_best;   // smallest score whose distance passes max_distance (INT32_MAX if none)
+  int32_t min_score;  // smallest score that can change any decision, clamped to >= 1
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct smb_result {
+  std::vector<PairOut> pair_out;  // per pair: start/count into matches
+  smb_match* matches = nullptr;   // pinned
+  size_t matches_cap = 0;
+  size_t total = 0;
+};
+
+struct smb_handle {
+  int device = -1;
+  int num_sms = 0;
+  smb_options opts{};
+  float max_ratio_f = 0.f, max_distance_f = 0.f;
+  Filter filter{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
+
+  // descriptor pool
+  uint8_t* pool = nullptr;
+  uint32_t pool_rows = 0;
+  std::map<uint32_t, uint32_t> free_list;  // row0 -> rows (coalesced)
+  std::unordered_map<uint64_t, ImageEntry> images;
+  CUtensorMap tmap{};
+  bool tmap_valid = false;
+
+  // acos table
+  std::vector<float> lut_host;
+  float* lut_dev = nullptr;
+
+  // per-call scratch
+  DevBuf<PairMeta> d_pairs;
+  DevBuf<WorkItem> d_items;
+  DevBuf<TopTwo> d_acc;
+  DevBuf<uint2> d_out;
+  DevBuf<PairOut> d_pair_out;
+  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates
+  PinnedBuf<PairMeta> h_pairs;
+  PinnedBuf<WorkItem> h_items;
+  PinnedBuf<PairOut> h_pair_out;
+  unsigned long long* h_counters = nullptr;  // pinned [2]
+
+  std::vector<smb_result*> result_pool;
+  smb_timing timing{};
+  size_t acc_budget = (size_t)64 << 20;  // accumulator entries per internal batch (16 B each)
+
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+};
+
+namespace {
+
+int fail(smb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define SMB_CUDA(h, expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail((h), e__ == cudaErrorMemoryAllocation ? SMB_ENOMEM : SMB_ECUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Filter derivation.  lut[d] = acosf(min(d * 2^-18, 1)) computed by THIS process' libm, i.e. the
+// very function COLMAP's FindBestMatchesOneWay evaluates; the device only ever looks values up.
+//
+//   min_best  = min{ d : lut[d] <= max_distance }                      (best below it fails test 1)
+//   M         = max{ lut[d] : lut[d] <= max_distance }                 (largest passing distance)
+//   min_second= min{ s : max_ratio * lut[s] <= M }                     (second below it can never
+//                                                                       make test 2 reject)
+//   min_score = max(1, min(min_best, min_second))
+//
+// No monotonicity of lut is assumed.  Scores below min_score are dropped before the top-2
+// accumulators; DESIGN.md ("Filter") proves every FeatureMatch is unchanged.
+// ------------------------------------------------------------------------------------------
+Filter derive_filter(const std::vector<float>& lut, float max_ratio, float max_distance) {
+  Filter f;
+  int64_t min_best = -1;
+  float M = -1.f;
+  for (int d = 0; d < kLutSize; ++d) {
+    if (lut[d] <= max_distance) {
+      if (min_best < 0) min_best = d;
+      M = std::max(M, lut[d]);
+    }
+  }
+  if (min_best < 0) {  // nothing can ever pass max_distance (also covers NaN thresholds)
+    f.min_best = INT32_MAX;
+    f.min_score = INT32_MAX;
+    return f;
+  }
+  int64_t min_second = kLutSize;  // scores >= 512^2 share lut[512^2]; handled by the loop's last entry
+  for (int s = 0; s < kLutSize; ++s) {
+    const float rhs = max_ratio * lut[s];
+    if (!(M < rhs)) {  // "best_normed >= max_ratio * second_normed" possible (NaN-safe)
+      min_second = s;
+      break;
+    }
+  }
+  f.min_best = (int32_t)min_best;
+  f.min_score = (int32_t)std::max<int64_t>(1, std::min(min_best, min_second));
+  return f;
+}
+
+int apply_options(smb_handle* h, const smb_options* opts) {
+  if (!opts) return fail(h, SMB_EINVAL, "options pointer is null");
+  if (opts->engine != SMB_ENGINE_TCGEN05 && opts->engine != SMB_ENGINE_DP4A)
+    return fail(h, SMB_EINVAL, "unknown engine %d", opts->engine);
+  h->opts = *opts;
+  h->max_ratio_f = (float)opts->max_ratio;        // double -> float exactly where COLMAP narrows
+  h->max_distance_f = (float)opts->max_distance;
+  h->filter = derive_filter(h->lut_host, h->max_ratio_f, h->max_distance_f);
+  return SMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Descriptor pool: one device allocation of pool_rows x 128 B; images occupy row ranges padded to
+// kRowPad with zero rows (a zero descriptor scores 0 against everything and can never be a
+// candidate), so TMA boxes never need masking.
+// ------------------------------------------------------------------------------------------
+int encode_tmap(smb_handle* h) {
+  h->tmap_valid = false;
+  if (!h->pool_rows) return SMB_OK;
+  cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)h->pool_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kDim};
+  cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)kStripRows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = h->encode_tiled(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->pool, gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SMB_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  h->tmap_valid = true;
+  return SMB_OK;
+}
+
+void free_rows(smb_handle* h, uint32_t row0, uint32_t rows) {
+  if (!rows) return;
+  auto it = h->free_list.emplace(row0, rows).first;
+  auto nx = std::next(it);
+  if (nx != h->free_list.end() && it->first + it->second == nx->first) {
+    it->second += nx->second;
+    h->free_list.erase(nx);
+  }
+  if (it != h->free_list.begin()) {
+    auto pv = std::prev(it);
+    if (pv->first + pv->second == it->first) {
+      pv->second += it->second;
+      h->free_list.erase(it);
+    }
+  }
+}
+
+int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
+  uint64_t want = std::max<uint64_t>((uint64_t)h->pool_rows * 2, (uint64_t)h->pool_rows + min_extra_rows);
+  want = std::max<uint64_t>(want, (uint64_t)(64u << 20) / kDim);  // start at 64 MiB
+  want = (want + kRowPad - 1) / kRowPad * kRowPad;
+  if (want > 0xFFFFFF00ull) return fail(h, SMB_ENOMEM, "descriptor pool would exceed 2^32 rows");
+  uint8_t* np = nullptr;
+  SMB_CUDA(h, cudaMalloc(&np, want * kDim));
+  if (h->pool) {
+    SMB_CUDA(h, cudaMemcpyAsync(np, h->pool, (size_t)h->pool_rows * kDim, cudaMemcpyDeviceToDevice, h->stream));
+    SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMB_CUDA(h, cudaFree(h->pool));
+  }
+  const uint32_t old_rows = h->pool_rows;
+  h->pool = np;
+  h->pool_rows = (uint32_t)want;
+  free_rows(h, old_rows, (uint32_t)want - old_rows);
+  return encode_tmap(h);
+}
+
+int alloc_rows(smb_handle* h, uint32_t rows, uint32_t* row0) {
+  if (rows == 0) {
+    *row0 = 0;
+    return SMB_OK;
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (auto it = h->free_list.begin(); it != h->free_list.end(); ++it) {
+      if (it->second >= rows) {
+        *row0 = it->first;
+        const uint32_t rest = it->second - rows, rest0 = it->first + rows;
+        h->free_list.erase(it);
+        if (rest) h->free_list.emplace(rest0, rest);
+        return SMB_OK;
+      }
+    }
+    int rc = grow_pool(h, rows);
+    if (rc != SMB_OK) return rc;
+  }
+  return fail(h, SMB_ENOMEM, "descriptor pool allocation of %u rows failed", rows);
+}
+
+int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_t d, cudaMemcpyKind kind) {
+  if (d != (size_t)kDim) return fail(h, SMB_EINVAL, "descriptor dimension must be 128, got %zu", d);
+  if (n && !src) return fail(h, SMB_EINVAL, "descriptor pointer is null");
+  if (n > 0x7FFFFFFFu) return fail(h, SMB_EINVAL, "too many descriptors in one image: %zu", n);
+  auto old = h->images.find(key);
+  if (old != h->images.end()) {
+    // pairs already queued on the stream may still read the old rows
+    SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    free_rows(h, old->second.row0, old->second.rows);
+    h->images.erase(old);
+  }
+  ImageEntry e;
+  e.n = (uint32_t)n;
+  e.rows = (uint32_t)((n + kRowPad - 1) / kRowPad * kRowPad);
+  int rc = alloc_rows(h, e.rows, &e.row0);
+  if (rc != SMB_OK) return rc;
+  if (n) {
+    uint8_t* dst = h->pool + (size_t)e.row0 * kDim;
+    SMB_CUDA(h, cudaMemcpyAsync(dst, src, n * kDim, kind, h->stream));
+    if (e.rows > n) SMB_CUDA(h, cudaMemsetAsync(dst + n * kDim, 0, (size_t)(e.rows - n) * kDim, h->stream));
+  }
+  h->images.emplace(key, e);
+  return SMB_OK;
+}
+
+smb_result* acquire_result(smb_handle* h) {
+  if (!h->result_pool.empty()) {
+    smb_result* r = h->result_pool.back();
+    h->result_pool.pop_back();
+    return r;
+  }
+  return new (std::nothrow) smb_result();
+}
+
+struct BatchPlan {
+  size_t first, last;  // pair index range [first, last)
+};
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+void smb_default_options(smb_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->max_ratio = 0.8;       // colmap.proto:14
+  o->max_distance = 0.7;    // colmap.proto:17
+  o->cross_check = 1;       // colmap.proto:20
+  o->max_num_matches = 32768;  // colmap.proto:23
+  o->engine = SMB_ENGINE_TCGEN05;
+  o->profile = 0;
+}
+
+int smb_abi_version(void) { return SMB_ABI_VERSION; }
+
+const char* smb_last_error(const smb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
+  if (!out) return fail(nullptr, SMB_EINVAL, "out pointer is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(nullptr, SMB_ENODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (cuda_device < 0 || cuda_device >= count)
+    return fail(nullptr, SMB_EINVAL, "cuda_device %d out of range [0, %d)", cuda_device, count);
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, cuda_device);
+  if (ce != cudaSuccess) return fail(nullptr, SMB_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce));
+  if (prop.major != 10)
+    return fail(nullptr, SMB_ENODEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", cuda_device,
+                prop.name, prop.major, prop.minor);
+  smb_handle* h = new (std::nothrow) smb_handle();
+  if (!h) return fail(nullptr, SMB_ENOMEM, "out of host memory");
+  h->device = cuda_device;
+  h->num_sms = prop.multiProcessorCount;
+  int rc = SMB_OK;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    smb_destroy(h);
+    return code;
+  };
+#define SMB_CUDA_C(expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return bail(SMB_ECUDA);                                                                \
+    }                                                                                        \
+  } while (0)
+  SMB_CUDA_C(cudaSetDevice(cuda_device));
+  SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) SMB_CUDA_C(cudaEventCreate(&e));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SMB_CUDA_C(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      fail(h, SMB_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+      return bail(SMB_ECUDA);
+    }
+    h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  // the acos table: host libm, the same function the reference evaluates
+  h->lut_host.resize(kLutSize);
+  {
+    const float kDistNorm = 1.0f / (512.0f * 512.0f);
+    for (int d = 0; d < kLutSize; ++d) h->lut_host[d] = acosf(std::min(kDistNorm * (float)d, 1.0f));
+  }
+  SMB_CUDA_C(cudaMalloc(&h->lut_dev, kLutSize * sizeof(float)));
+  SMB_CUDA_C(cudaMemcpyAsync(h->lut_dev, h->lut_host.data(), kLutSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  SMB_CUDA_C(cudaMalloc(&h->d_counters, 2 * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMallocHost(&h->h_counters, 2 * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
+  SMB_CUDA_C(cudaStreamSynchronize(h->stream));
+#undef SMB_CUDA_C
+  smb_options def;
+  smb_default_options(&def);
+  rc = apply_options(h, opts ? opts : &def);
+  if (rc != SMB_OK) return bail(rc);
+  *out = h;
+  return SMB_OK;
+}
+
+void smb_destroy(smb_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (smb_result* r : h->result_pool) {
+    if (r->matches) cudaFreeHost(r->matches);
+    delete r;
+  }
+  h->d_pairs.release();
+  h->d_items.release();
+  h->d_acc.release();
+  h->d_out.release();
+  h->d_pair_out.release();
+  h->h_pairs.release();
+  h->h_items.release();
+  h->h_pair_out.release();
+  if (h->d_counters) cudaFree(h->d_counters);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->lut_dev) cudaFree(h->lut_dev);
+  if (h->pool) cudaFree(h->pool);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int smb_set_options(smb_handle* h, const smb_options* opts) {
+  if (!h) return SMB_EINVAL;
+  return apply_options(h, opts);
+}
+
+int smb_put_image(smb_handle* h, uint32_t image_id, const uint8_t* desc, size_t n, size_t d) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  int rc = put_image_impl(h, image_id, desc, n, d, cudaMemcpyHostToDevice);
+  if (rc != SMB_OK) return rc;
+  // the caller's buffer (Scanner-owned, valid only for the execute() call) is free again on return
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
+int smb_put_images(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
+                   size_t count, size_t d) {
+  if (!h) return SMB_EINVAL;
+  if (count && (!image_ids || !descs || !ns)) return fail(h, SMB_EINVAL, "null array argument");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  for (size_t k = 0; k < count; ++k) {
+    int rc = put_image_impl(h, image_ids[k], descs[k], ns[k], d, cudaMemcpyHostToDevice);
+    if (rc != SMB_OK) return rc;
+  }
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
+int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  int rc = put_image_impl(h, image_id, dev_desc, n, d, cudaMemcpyDefault);
+  if (rc != SMB_OK) return rc;
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
+int smb_has_image(const smb_handle* h, uint32_t image_id) { return h && h->images.count(image_id) ? 1 : 0; }
+
+int smb_evict_image(smb_handle* h, uint32_t image_id) {
+  if (!h) return SMB_EINVAL;
+  auto it = h->images.find(image_id);
+  if (it == h->images.end()) return fail(h, SMB_EINVAL, "image %u is not cached", image_id);
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_rows(h, it->second.row0, it->second.rows);
+  h->images.erase(it);
+  return SMB_OK;
+}
+
+int smb_clear_images(smb_handle* h) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->images.clear();
+  h->free_list.clear();
+  if (h->pool_rows) h->free_list.emplace(0u, h->pool_rows);
+  return SMB_OK;
+}
+
+int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** dev_ptr, size_t* n) {
+  if (!h || !dev_ptr || !n) return SMB_EINVAL;
+  auto it = h->images.find(image_id);
+  if (it == h->images.end()) return fail(const_cast<smb_handle*>(h), SMB_EINVAL, "image %u is not cached", image_id);
+  *dev_ptr = it->second.n ? h->pool + (size_t)it->second.row0 * kDim : nullptr;
+  *n = it->second.n;
+  return SMB_OK;
+}
+
+static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, size_t npairs, smb_result** out) {
+  *out = nullptr;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  const bool prof = h->opts.profile != 0;
+  const bool cc = h->opts.cross_check != 0;
+  std::memset(&h->timing, 0, sizeof h->timing);
+
+  smb_result* res = acquire_result(h);
+  if (!res) return fail(h, SMB_ENOMEM, "out of host memory");
+  auto give_back = [&](int code) {
+    h->result_pool.push_back(res);
+    return code;
+  };
+  res->pair_out.assign(npairs, PairOut{0, 0});
+  res->total = 0;
+  if (npairs == 0) {
+    *out = res;
+    return SMB_OK;
+  }
+  if (npairs > 0x7FFFFFFFull) return give_back(fail(h, SMB_EINVAL, "too many pairs in one call"));
+
+  // ---- plan: metas, output capacity, internal batches bounded by the accumulator budget
+  int rc = SMB_OK;
+  if (cudaSuccess != h->h_pairs.reserve(npairs)) return give_back(fail(h, SMB_ENOMEM, "pinned allocation failed"));
+  std::vector<BatchPlan> batches;
+  size_t out_cap = 0, n_items_total = 0, max_items = 0, max_acc = 0, max_pairs = 0;
+  {
+    size_t b_first = 0, b_acc = 0, b_items = 0;
+    for (size_t p = 0; p < npairs; ++p) {
+      auto i1 = h->images.find(keys[2 * p]);
+      auto i2 = h->images.find(keys[2 * p + 1]);
+      if (i1 == h->images.end() || i2 == h->images.end())
+        return give_back(fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", p,
+                              (unsigned long long)(i1 == h->images.end() ? keys[2 * p] : keys[2 * p + 1])));
+      const ImageEntry &a = i1->second, &b = i2->second;
+      const size_t need = (size_t)a.n + b.n;
+      if (p > b_first && b_acc + need > h->acc_budget) {
+        batches.push_back({b_first, p});
+        max_items = std::max(max_items, b_items);
+        max_acc = std::max(max_acc, b_acc);
+        max_pairs = std::max(max_pairs, p - b_first);
+        b_first = p;
+        b_acc = 0;
+        b_items = 0;
+      }
+      PairMeta& m = h->h_pairs.p[p];
+      m.a_row0 = a.row0;
+      m.n1 = a.n;
+      m.b_row0 = b.row0;
+      m.n2 = b.n;
+      m.acc_off = b_acc;
+      m.out_slot = (uint32_t)p;
+      m.pad_ = 0;
+      b_acc += need;
+      if (a.n && b.n) b_items += (a.n + kStripRows - 1) / kStripRows;
+      out_cap += cc ? std::min(a.n, b.n) : a.n;
+    }
+    batches.push_back({b_first, npairs});
+    max_items = std::max(max_items, b_items);
+    max_acc = std::max(max_acc, b_acc);
+    max_pairs = std::max(max_pairs, npairs - b_first);
+  }
+  if (out_cap > 0xFFFFFFFFull) return give_back(fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call"));
+
+  if (cudaSuccess != h->d_pairs.reserve(max_pairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(max_items, 1)) ||
+      cudaSuccess != h->d_acc.reserve(std::max<size_t>(max_acc, 1)) || cudaSuccess != h->d_out.reserve(std::max<size_t>(out_cap, 1)) ||
+      cudaSuccess != h->d_pair_out.reserve(npairs) || cudaSuccess != h->h_pair_out.reserve(npairs) ||
+      cudaSuccess != h->h_items.reserve(std::max<size_t>(max_items, 1))) {
+    cudaGetLastError();
+    return give_back(fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu out=%zu)", npairs,
+                          max_acc, out_cap));
+  }
+
+  cudaStream_t st = h->stream;
+#define SMB_CUDA_R(expr)                                                                                  \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+      return give_back(fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+
+  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
+  SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned long long), st));
+  float score_ms = 0.f, decide_ms = 0.f;
+  uint64_t ops = 0;
+
+  for (const BatchPlan& bp : batches) {
+    const size_t np = bp.last - bp.first;
+    // work items: one per 128-row strip, pairs in caller order (strips of a pair stay adjacent so
+    // concurrently running CTAs stream the same image 2 out of L2), largest column counts first
+    size_t ni = 0, acc_entries = 0;
+    for (size_t p = bp.first; p < bp.last; ++p) {
+      const PairMeta& m = h->h_pairs.p[p];
+      acc_entries += (size_t)m.n1 + m.n2;
+      ops += 2ull * m.n1 * m.n2 * kDim;
+      if (!m.n1 || !m.n2) continue;
+      const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
+      for (uint32_t r = 0; r < m.n1; r += kStripRows)
+        h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first)};
+    }
+    std::stable_sort(h->h_items.p, h->h_items.p + ni,
+                     [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
+    n_items_total += ni;
+
+    SMB_CUDA_R(cudaMemcpyAsync(h->d_pairs.p, h->h_pairs.p + bp.first, np * sizeof(PairMeta), cudaMemcpyHostToDevice, st));
+    if (ni) SMB_CUDA_R(cudaMemcpyAsync(h->d_items.p, h->h_items.p, ni * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    if (acc_entries) SMB_CUDA_R(cudaMemsetAsync(h->d_acc.p, 0, acc_entries * sizeof(TopTwo), st));
+
+    if (ni) {
+      if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[2], st));
+      unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
+      if (h->opts.engine == SMB_ENGINE_TCGEN05) {
+        if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
+        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);
+        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
+                                                                          h->d_acc.p, h->filter.min_score, cand);
+      } else {
+        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
+        score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p, h->d_acc.p,
+                                                         h->filter.min_score, cand);
+      }
+      SMB_CUDA_R(cudaGetLastError());
+      h->timing.score_launches++;
+      h->timing.total_launches++;
+      if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[3], st));
+    }
+    if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[4], st));
+    decide_kernel<<<(unsigned)np, kDecideThreads, 0, st>>>(h->d_pairs.p, h->d_acc.p, h->lut_dev, h->max_ratio_f,
+                                                          h->max_distance_f, cc ? 1 : 0, h->d_out.p, h->d_counters,
+                                                          h->d_pair_out.p);
+    SMB_CUDA_R(cudaGetLastError());
+    h->timing.total_launches++;
+    if (prof) {
+      SMB_CUDA_R(cudaEventRecord(h->ev[5], st));
+      SMB_CUDA_R(cudaEventSynchronize(h->ev[5]));
+      float ms = 0.f;
+      if (ni) {
+        SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+        score_ms += ms;
+      }
+      SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+      decide_ms += ms;
+    } else if (batches.size() > 1) {
+      // the next batch reuses d_pairs / d_items / h_items
+      SMB_CUDA_R(cudaStreamSynchronize(st));
+    }
+  }
+
+  // ---- results: header first (sizes), then exactly the matches that exist
+  SMB_CUDA_R(cudaMemcpyAsync(h->h_pair_out.p, h->d_pair_out.p, npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+  SMB_CUDA_R(cudaMemcpyAsync(h->h_counters, h->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  SMB_CUDA_R(cudaStreamSynchronize(st));
+  const size_t total = (size_t)h->h_counters[0];
+  if (total > out_cap) return give_back(fail(h, SMB_ECUDA, "internal error: %zu matches exceed capacity %zu", total, out_cap));
+  if (total > res->matches_cap) {
+    if (res->matches) cudaFreeHost(res->matches);
+    res->matches = nullptr;
+    res->matches_cap = 0;
+    size_t want = std::max<size_t>(total, 4096);
+    SMB_CUDA_R(cudaMallocHost(&res->matches, want * sizeof(smb_match)));
+    res->matches_cap = want;
+  }
+  if (total) SMB_CUDA_R(cudaMemcpyAsync(res->matches, h->d_out.p, total * sizeof(smb_match), cudaMemcpyDeviceToHost, st));
+  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[1], st));
+  SMB_CUDA_R(cudaStreamSynchronize(st));
+  std::memcpy(res->pair_out.data(), h->h_pair_out.p, npairs * sizeof(PairOut));
+  res->total = total;
+  if (prof) {
+    float ms = 0.f;
+    SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->timing.total_ms = ms;
+    h->timing.score_ms = score_ms;
+    h->timing.decide_ms = decide_ms;
+    h->timing.candidates = h->h_counters[1];
+  }
+  h->timing.ops = ops;
+  (void)n_items_total;
+  (void)rc;
+#undef SMB_CUDA_R
+  *out = res;
+  return SMB_OK;
+}
+
+int smb_match_pairs(smb_handle* h, const uint32_t* pairs, size_t npairs, smb_result** out) {
+  if (!h) return SMB_EINVAL;
+  if (!out) return fail(h, SMB_EINVAL, "out pointer is null");
+  if (npairs && !pairs) return fail(h, SMB_EINVAL, "pairs pointer is null");
+  std::vector<uint64_t> keys(2 * npairs);
+  for (size_t k = 0; k < 2 * npairs; ++k) keys[k] = pairs[k];
+  return match_keys(h, keys.data(), npairs, out);
+}
+
+size_t smb_result_num_pairs(const smb_result* r) { return r ? r->pair_out.size() : 0; }
+
+const smb_match* smb_result_matches(const smb_result* r, size_t i, size_t* count) {
+  if (!r || i >= r->pair_out.size()) {
+    if (count) *count = 0;
+    return nullptr;
+  }
+  if (count) *count = r->pair_out[i].count;
+  return r->matches ? r->matches + r->pair_out[i].start : nullptr;
+}
+
+size_t smb_result_total_matches(const smb_result* r) { return r ? r->total : 0; }
+
+void smb_result_release(smb_handle* h, smb_result* r) {
+  if (!r) return;
+  if (h) {
+    h->result_pool.push_back(r);
+  } else {
+    if (r->matches) cudaFreeHost(r->matches);
+    delete r;
+  }
+}
+
+int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const uint8_t* desc2, size_t n2,
+                          smb_match* out, size_t capacity, size_t* count) {
+  if (!h) return SMB_EINVAL;
+  if (!count) return fail(h, SMB_EINVAL, "count pointer is null");
+  *count = 0;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  const uint64_t k1 = 1ull << 32, k2 = (1ull << 32) + 1;  // private ids, cannot collide with uint32 image ids
+  int rc = put_image_impl(h, k1, desc1, n1, kDim, cudaMemcpyHostToDevice);
+  if (rc == SMB_OK) rc = put_image_impl(h, k2, desc2, n2, kDim, cudaMemcpyHostToDevice);
+  smb_result* res = nullptr;
+  if (rc == SMB_OK) {
+    const uint64_t keys[2] = {k1, k2};
+    rc = match_keys(h, keys, 1, &res);
+  }
+  if (rc == SMB_OK) {
+    size_t c = 0;
+    const smb_match* m = smb_result_matches(res, 0, &c);
+    if (c > capacity) {
+      rc = fail(h, SMB_ECAPACITY, "output capacity %zu < %zu matches", capacity, c);
+    } else {
+      if (c) std::memcpy(out, m, c * sizeof(smb_match));
+      *count = c;
+    }
+    smb_result_release(h, res);
+  }
+  cudaStreamSynchronize(h->stream);
+  for (uint64_t k : {k1, k2}) {
+    auto it = h->images.find(k);
+    if (it != h->images.end()) {
+      free_rows(h, it->second.row0, it->second.rows);
+      h->images.erase(it);
+    }
+  }
+  return rc;
+}
+
+int smb_get_timing(const smb_handle* h, smb_timing* t) {
+  if (!h || !t) return SMB_EINVAL;
+  *t = h->timing;
+  return SMB_OK;
+}
+
+int smb_get_filter(const smb_handle* h, int32_t* min_score, int32_t* min_best) {
+  if (!h) return SMB_EINVAL;
+  if (min_score) *min_score = h->filter.min_score;
+  if (min_best) *min_best = h->filter.min_best;
+  return SMB_OK;
+}
+
+void* smb_stream(const smb_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int smb_synchronize(smb_handle* h) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
+}  // extern "C"

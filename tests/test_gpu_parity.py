@@ -1,0 +1,175 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle,
+bit-exact on every FeatureMatch.  Reference call being replaced:
+/root/reference/integration/op_cpp/sequential_matching.cc:154 (colmap::MatchSiftFeaturesCPU)."""
+import numpy as np
+import pytest
+
+from scanner_colmap_b200 import SiftMatcher, synth, sequential_pairs
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["tcgen05", "dp4a"]
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    from oracle import oracle as o
+    return o
+
+
+def _check_pairs(oracle, m, imgs, ids, pairs, **opts):
+    got = m.match_pairs(pairs)
+    id2k = {i: k for k, i in enumerate(ids)}
+    kp = [(id2k[int(a)], id2k[int(b)]) for a, b in pairs]
+    want, _ = oracle.match_many(imgs, kp, **opts)
+    assert len(got) == len(want)
+    for (a, b), g, w in zip(pairs, got, want):
+        assert g.dtype == np.uint32 and g.shape[1] == 2
+        assert np.array_equal(g, w), f"pair ({a},{b}): {len(g)} vs oracle {len(w)} matches"
+    return sum(len(g) for g in got)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_small_sequential_window(oracle, engine):
+    ids = list(range(100, 108))
+    sizes = [300, 256, 257, 1, 129, 1000, 127, 640]
+    imgs = [synth.make_image(i, n, track_step=32) for i, n in zip(ids, sizes)]
+    pairs = sequential_pairs(ids, 4)
+    with SiftMatcher(engine=engine) as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+    assert total > 0
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n1,n2", [(0, 5), (5, 0), (0, 0), (1, 1), (127, 129), (128, 256), (129, 127), (255, 257),
+                                   (4095, 4097), (4097, 4095)])
+def test_ragged_edge_shapes(oracle, engine, n1, n2):
+    a = synth.make_image(1, n1, track_step=8)
+    b = synth.make_image(2, n2, track_step=8)
+    with SiftMatcher(engine=engine) as m:
+        got = m.match(a, b)
+    want = oracle.match(a, b)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("cross_check", [True, False])
+@pytest.mark.parametrize("max_ratio,max_distance", [(0.8, 0.7), (0.95, 1.2), (0.6, 0.5), (1.0, 1.5707964), (0.0, 0.7),
+                                                    (0.8, 0.0), (2.0, 3.0)])
+def test_option_sweep(oracle, engine, cross_check, max_ratio, max_distance):
+    """Thresholds move the integer pre-filter (down to 'every positive score is a candidate'): results stay exact."""
+    a = synth.make_image(10, 600, track_step=16, noise=0.25)
+    b = synth.make_image(11, 520, track_step=16, noise=0.25)
+    with SiftMatcher(engine=engine, max_ratio=max_ratio, max_distance=max_distance, cross_check=cross_check) as m:
+        got = m.match(a, b)
+    want = oracle.match(a, b, max_ratio=max_ratio, max_distance=max_distance, cross_check=cross_check)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_adversarial_inputs(oracle, engine):
+    rng = np.random.default_rng(7)
+    base = synth.make_image(3, 300, track_step=8)
+    cases = {
+        "all_identical": (np.tile(base[:1], (260, 1)), np.tile(base[:1], (300, 1))),      # every score ties
+        "all_zero": (np.zeros((130, 128), np.uint8), np.zeros((140, 128), np.uint8)),     # no positive score
+        "zero_vs_real": (np.zeros((130, 128), np.uint8), base),
+        "duplicated_rows": (base, np.concatenate([base[:150], base[:150]])),              # tie -> lowest index... and best==second
+        "saturating": (rng.integers(200, 256, (257, 128), dtype=np.uint8),                # dot >> 512^2: acos saturates
+                       rng.integers(200, 256, (255, 128), dtype=np.uint8)),
+        "uniform_random": (rng.integers(0, 256, (300, 128), dtype=np.uint8),
+                           rng.integers(0, 256, (280, 128), dtype=np.uint8)),
+        "max_value": (np.full((129, 128), 255, np.uint8), np.full((131, 128), 255, np.uint8)),
+        "self_match": (base, base.copy()),
+    }
+    with SiftMatcher(engine=engine) as m:
+        for name, (a, b) in cases.items():
+            for cc in (True, False):
+                m.set_options(cross_check=cc)
+                got = m.match(a, b)
+                want = oracle.match(a, b, cross_check=cc)
+                assert np.array_equal(got, want), f"{name} cross_check={cc}: {len(got)} vs {len(want)}"
+    # the self-match case must be non-trivial
+    assert len(oracle.match(base, base.copy())) > 100
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_saturated_scores_keep_argmax(oracle, engine):
+    """Scores above 512^2 all map to distance 0, but the best index must still be the true arg-max
+    (lowest index among equal maxima), so saturated scores may not be clamped before the top-2."""
+    a = np.zeros((3, 128), np.uint8)
+    a[:, :8] = 250
+    b = np.zeros((300, 128), np.uint8)
+    b[:, :8] = 100
+    b[137, :8] = 255
+    b[20, :8] = 254
+    with SiftMatcher(engine=engine, cross_check=False, max_ratio=1.5, max_distance=2.0) as m:
+        got = m.match(a, b)
+    want = oracle.match(a, b, cross_check=False, max_ratio=1.5, max_distance=2.0)
+    assert np.array_equal(got, want)
+
+
+def test_engines_agree_and_cache_semantics(oracle):
+    ids = [5, 9, 4000000000]
+    imgs = [synth.make_image(i % 1000, n, track_step=16) for i, n in zip(ids, (512, 400, 300))]
+    pairs = np.array([[5, 9], [9, 5], [5, 4000000000], [5, 5]], dtype=np.uint32)
+    with SiftMatcher() as m:
+        m.put_images(ids, imgs)
+        assert m.has_image(9) and not m.has_image(10)
+        _check_pairs(oracle, m, imgs, ids, pairs)
+        # replace an image: later pairs must see the new descriptors
+        imgs[1] = synth.make_image(77, 650, track_step=16)
+        m.put_image(9, imgs[1])
+        _check_pairs(oracle, m, imgs, ids, pairs)
+        m.evict_image(9)
+        with pytest.raises(Exception):
+            m.match_pairs(pairs)
+        ptr, n = m.image_device_ptr(5)
+        assert ptr != 0 and n == 512
+        m.put_image_device(6, ptr, n)  # device-to-device put (the halo path)
+        ids2, imgs2 = [5, 6], [imgs[0], imgs[0]]
+        _check_pairs(oracle, m, imgs2, ids2, np.array([[5, 6]], dtype=np.uint32))
+
+
+def test_config1_20x4096_overlap10(oracle):
+    """BASELINE.json configs[0]: 20 images x 4096, overlap=10 -> 135 pairs, every FeatureMatch bit-exact."""
+    ids = list(range(20))
+    imgs = synth.make_images(20, 4096)
+    pairs = sequential_pairs(ids, 10)
+    assert len(pairs) == 135
+    with SiftMatcher(profile=True) as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+        t = m.timing()
+    assert total > 1000
+    assert t["score_launches"] >= 1 and t["ops"] == 135 * 2 * 4096 * 4096 * 128
+
+
+def test_pool_growth_and_many_images(oracle):
+    """More descriptor bytes than the initial 64 MiB pool: the pool grows, rows stay valid."""
+    ids = list(range(70))
+    imgs = [synth.make_image(i, 8192 if i % 2 else 8000, track_step=512) for i in ids]
+    with SiftMatcher() as m:
+        for i, d in zip(ids, imgs):
+            m.put_image(i, d)
+        pairs = np.array([[0, 1], [33, 34], [68, 69], [1, 69]], dtype=np.uint32)
+        _check_pairs(oracle, m, imgs, ids, pairs)
+
+
+def test_full_size_properties_8192():
+    """BASELINE full size (8192 x 8192) through size-independent properties: symmetry of cross-checked
+    matching under swapping the images, idempotence, and self-matching = identity on distinct rows."""
+    a = synth.make_image(0, 8192)
+    b = synth.make_image(1, 8192)
+    with SiftMatcher() as m:
+        m.put_images([0, 1], [a, b])
+        ab, ba, ab2, aa = m.match_pairs(np.array([[0, 1], [1, 0], [0, 1], [0, 0]], dtype=np.uint32))
+    assert len(ab) > 1000
+    assert np.array_equal(ab, ab2)
+    swapped = ba[:, ::-1]
+    swapped = swapped[np.argsort(swapped[:, 0], kind="stable")]
+    assert np.array_equal(ab, swapped)            # cross-check makes the relation symmetric
+    assert np.all(np.diff(ab[:, 0].astype(np.int64)) > 0)  # ascending idx1, unique
+    assert len(np.unique(ab[:, 1])) == len(ab)    # one-to-one
+    assert np.array_equal(aa[:, 0], aa[:, 1])     # an image matched with itself pairs each row with itself
