@@ -23,7 +23,7 @@
 namespace smb {
 
 constexpr int kDim = 128;            // descriptor bytes == GEMM K
-constexpr int kStripRows = 128;      // rows of image 1 per work item == UMMA M
+constexpr int kStripRows = 256;      // rows of image 1 per work item (two UMMA M=128 row blocks)
 constexpr int kTileCols = 256;       // columns (rows of image 2) per accumulator tile == UMMA N
 constexpr int kRowPad = 256;         // every cached image occupies a multiple of this many pool rows
 constexpr int kLutSize = 512 * 512 + 1;
@@ -33,16 +33,16 @@ struct PairMeta {
   uint32_t n1;
   uint32_t b_row0;   // pool row of image 2
   uint32_t n2;
-  uint64_t acc_off;  // accumulators: rows at [acc_off, acc_off+n1), columns at [acc_off+n1, acc_off+n1+n2)
+  uint32_t acc_off;  // accumulator slots: rows at [acc_off, acc_off+n1), columns at [acc_off+n1, acc_off+n1+n2)
   uint32_t out_slot; // index into the per-call pair_out array
-  uint32_t pad_;
 };
 
-struct WorkItem {     // one 128-row strip of one pair against all of image 2
+struct WorkItem {     // one strip (<= 256 rows) of image 1 against all of image 2
   uint32_t a_row;     // pool row of the strip
   uint32_t b_row;     // pool row of image 2
   uint32_t n_btiles;  // number of 256-column tiles
   uint32_t pair;      // index into PairMeta (batch-local)
+  uint32_t m_tiles;   // 1 or 2 accumulator row blocks (128 rows each) in this strip
 };
 
 struct TopTwo {
@@ -55,59 +55,126 @@ struct PairOut {
   uint32_t count;
 };
 
-__device__ __forceinline__ unsigned long long make_key(int score, uint32_t idx) {
-  return (static_cast<unsigned long long>(static_cast<uint32_t>(score)) << 32) | static_cast<uint32_t>(~idx);
+// key = score << 32 | ~slot.  "slot" is the accumulator slot of the OTHER axis (column slot in a row
+// accumulator and vice versa); inside one pair slots are ordered like indices, so max(key) is "highest
+// score, then lowest index" and decide() recovers the index by subtracting the pair's base slot.
+__device__ __forceinline__ unsigned long long make_key(uint32_t score, uint32_t slot) {
+  return (static_cast<unsigned long long>(score) << 32) | static_cast<uint32_t>(~slot);
 }
 
-// Insert into a {best, runner-up} pair with two atomic max operations.  Keys are distinct (the
-// index is part of the key), k1 ends as the global maximum, and every insertion hands
-// min(previous best, key) to k2, so k2 ends as the second-largest key regardless of order.
-__device__ __forceinline__ void top2_insert(TopTwo* t, unsigned long long key) {
-  unsigned long long old = atomicMax(&t->k1, key);
-  unsigned long long loser = old < key ? old : key;
-  if (loser) atomicMax(&t->k2, loser);
-}
-
-// A score that survived the pre-filter: feed the row- and column-direction accumulators.
-__device__ __noinline__ void emit_candidate(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc,
-                                            uint32_t pair, uint32_t a_row, uint32_t row_in_strip, uint32_t col,
-                                            int score, unsigned long long* cand_counter) {
-  const PairMeta pm = pairs[pair];
-  const uint32_t i = a_row - pm.a_row0 + row_in_strip;
-  if (i >= pm.n1 || col >= pm.n2) return;  // pool padding
-  TopTwo* rows = acc + pm.acc_off;
-  top2_insert(rows + i, make_key(score, col));
-  top2_insert(rows + pm.n1 + col, make_key(score, i));
-  if (cand_counter) atomicAdd(cand_counter, 1ull);
+// Insert into {best, runner-up} accumulators of a row and a column with atomic max.  Keys are
+// distinct (the slot is part of the key); k1 ends as the maximum, and every insertion hands
+// min(previous best, key) to k2, so k2 ends as the second-largest key whatever the order.
+__device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t row_slot, uint32_t col_slot,
+                                             uint32_t score) {
+  TopTwo* tr = acc + row_slot;
+  TopTwo* tc = acc + col_slot;
+  const unsigned long long kr = make_key(score, col_slot), kc = make_key(score, row_slot);
+  const unsigned long long o_r = atomicMax(&tr->k1, kr);  // both round trips in flight together
+  const unsigned long long o_c = atomicMax(&tc->k1, kc);
+  const unsigned long long l_r = o_r < kr ? o_r : kr;
+  const unsigned long long l_c = o_c < kc ? o_c : kc;
+  if (l_r) atomicMax(&tr->k2, l_r);
+  if (l_c) atomicMax(&tc->k2, l_c);
 }
 
 // =====================================================================================
 // Production score kernel: TMA -> swizzled smem -> tcgen05.mma kind::i8 -> TMEM -> filter
+//
+//   warp 0      TMA producer: A strip (256 rows, kept for the whole item) + ring of B tiles (256 rows)
+//   warp 1      MMA issuer: per B tile two accumulator tiles (strip rows 0-127 / 128-255), 4 x K32 each,
+//               ping-pong between the two 256-column halves of TMEM
+//   warp 2      TMEM allocator, then candidate drain
+//   warp 3      candidate drain: pops the shared-memory queue and feeds the top-2 accumulators (global
+//               atomics) so their latency never sits in the tile pipeline
+//   warps 4-11  filter epilogue: tcgen05.ld + 3-input max tree; entries >= min_score -> queue
 // =====================================================================================
 constexpr int kStages = 4;                     // B-tile ring
 constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
-constexpr int kABytes = kStripRows * kDim;     // 16 KiB
-constexpr int kBBytes = kTileCols * kDim;      // 32 KiB
+constexpr int kMTile = 128;                    // UMMA M
+constexpr int kABytes = kStripRows * kDim;     // 32 KiB (two 128-row boxes)
+constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
 constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter
+constexpr int kDrainWarps = 2;
 constexpr int kScoreThreads = 32 * (4 + kEpiWarps);
-constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + 256 /*barriers*/;
+constexpr int kQueueSlots = 1024;              // candidate queue entries (16 B each)
 
-struct ScoreBarriers {
+struct Cand {
+  uint32_t row_slot, col_slot, score;
+  uint32_t flag;  // 2g = free for generation g, 2g+1 = holds the entry of generation g
+};
+
+struct ScoreShared {
   uint64_t a_full[kAStages], a_empty[kAStages];
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t t_full[2], t_empty[2];
   uint32_t tmem_base;
+  uint32_t q_tail;      // next queue slot to claim
+  uint32_t q_done;      // epilogue warps that have finished
+  uint32_t pad_;
+  Cand queue[kQueueSlots];
 };
-static_assert(sizeof(ScoreBarriers) <= 256, "barrier block");
+constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + (int)sizeof(ScoreShared);
 
-template <int N>
-__device__ __forceinline__ int max_tree(const uint32_t (&v)[N]) {
-  // 3-input integer max (VIMNMX3): 0.5 ALU instruction per accumulator element
-  int m = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+// max over 32 accumulator entries with 3-input integer max (VIMNMX3), as a tree for ILP:
+// 16 instructions per 32 entries
+__device__ __forceinline__ int max_tree32(const uint32_t (&v)[32]) {
+  int a[11];
 #pragma unroll
-  for (int e = 3; e + 1 < N; e += 2) m = __vimax3_s32(m, (int)v[e], (int)v[e + 1]);
-  if ((N - 3) & 1) m = max(m, (int)v[N - 1]);
-  return m;
+  for (int g = 0; g < 10; ++g) a[g] = __vimax3_s32((int)v[3 * g], (int)v[3 * g + 1], (int)v[3 * g + 2]);
+  a[10] = max((int)v[30], (int)v[31]);
+  const int b0 = __vimax3_s32(a[0], a[1], a[2]);
+  const int b1 = __vimax3_s32(a[3], a[4], a[5]);
+  const int b2 = __vimax3_s32(a[6], a[7], a[8]);
+  const int b3 = max(a[9], a[10]);
+  return max(__vimax3_s32(b0, b1, b2), b3);
+}
+
+__device__ __forceinline__ void queue_push(ScoreShared* sh, uint32_t row_slot, uint32_t col_slot, uint32_t score) {
+  const uint32_t s = atomicAdd(&sh->q_tail, 1u);
+  Cand* c = &sh->queue[s % kQueueSlots];
+  const uint32_t gen2 = (s / kQueueSlots) * 2;
+  volatile uint32_t* flag = &c->flag;
+  uint32_t spins = 0;
+  while (*flag != gen2) {  // previous occupant not drained yet (queue full): back-pressure
+    if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
+  }
+  c->row_slot = row_slot;
+  c->col_slot = col_slot;
+  c->score = score;
+  __threadfence_block();
+  *flag = gen2 + 1;
+}
+
+__device__ __forceinline__ void drain_loop(ScoreShared* sh, TopTwo* __restrict__ acc, uint32_t drain_lane,
+                                           unsigned long long* cand_counter) {
+  uint32_t idx = drain_lane;  // this lane owns queue slots idx, idx + 32*kDrainWarps, ...
+  uint32_t count = 0;
+  volatile uint32_t* tail = &sh->q_tail;
+  volatile uint32_t* done = &sh->q_done;
+  for (;;) {
+    Cand* c = &sh->queue[idx % kQueueSlots];
+    volatile uint32_t* flag = &c->flag;
+    const uint32_t want = (idx / kQueueSlots) * 2 + 1;
+    bool got = false;
+    if (*flag == want) {
+      __threadfence_block();
+      const uint32_t r = *(volatile uint32_t*)&c->row_slot;
+      const uint32_t cs = *(volatile uint32_t*)&c->col_slot;
+      const uint32_t sc = *(volatile uint32_t*)&c->score;
+      __threadfence_block();
+      *flag = want + 1;  // free for the next generation
+      top2_insert2(acc, r, cs, sc);
+      idx += 32 * kDrainWarps;
+      ++count;
+      got = true;
+    } else if (*done == kEpiWarps) {
+      __threadfence_block();
+      if (idx >= *tail) break;  // q_done is bumped only after every push of that warp is visible
+    }
+    if (!got) __nanosleep(128);
+  }
+  if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
 }
 
 __global__ void __launch_bounds__(kScoreThreads, 1)
@@ -118,8 +185,8 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem0;
   const uint32_t smem_b = smem0 + kAStages * kABytes;
-  ScoreBarriers* bars =
-      reinterpret_cast<ScoreBarriers*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes + kStages * kBBytes);
+  ScoreShared* sh =
+      reinterpret_cast<ScoreShared*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes + kStages * kBBytes);
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
@@ -127,27 +194,30 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap);
     for (int s = 0; s < kAStages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->a_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->a_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->a_empty[s]), 1);
     }
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->b_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->t_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->t_empty[s]), kEpiWarps);
+      ptx::mbar_init(ptx::smem_u32(&sh->t_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), kEpiWarps);
     }
+    sh->q_tail = 0;
+    sh->q_done = 0;
     ptx::fence_barrier_init();
   }
+  for (uint32_t x = threadIdx.x; x < kQueueSlots; x += kScoreThreads) sh->queue[x].flag = 0;
   if (warp == 2) {  // whole warp: TMEM allocation (all 512 columns: two 256-column accumulators)
-    ptx::tmem_alloc_512(ptx::smem_u32(&bars->tmem_base));
+    ptx::tmem_alloc_512(ptx::smem_u32(&sh->tmem_base));
     ptx::tmem_relinquish();
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = sh->tmem_base;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one lane)
@@ -155,13 +225,15 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[as]), aph ^ 1);
-        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bars->a_full[as]), kABytes);
-        ptx::tma_load_2d(smem_a + as * kABytes, &tmap, ptx::smem_u32(&bars->a_full[as]), 0, (int32_t)w.a_row);
+        ptx::mbar_wait(ptx::smem_u32(&sh->a_empty[as]), aph ^ 1);
+        const uint32_t afull = ptx::smem_u32(&sh->a_full[as]);
+        ptx::mbar_arrive_expect_tx(afull, w.m_tiles * (kABytes / 2));
+        for (uint32_t mh = 0; mh < w.m_tiles; ++mh)
+          ptx::tma_load_2d(smem_a + as * kABytes + mh * (kABytes / 2), &tmap, afull, 0, (int32_t)(w.a_row + mh * kMTile));
         if (++as == kAStages) { as = 0; aph ^= 1; }
         for (uint32_t t = 0; t < w.n_btiles; ++t) {
-          ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[bs]), bph ^ 1);
-          const uint32_t full = ptx::smem_u32(&bars->b_full[bs]);
+          ptx::mbar_wait(ptx::smem_u32(&sh->b_empty[bs]), bph ^ 1);
+          const uint32_t full = ptx::smem_u32(&sh->b_full[bs]);
           ptx::mbar_arrive_expect_tx(full, kBBytes);
           const int32_t r = (int32_t)(w.b_row + t * kTileCols);
           ptx::tma_load_2d(smem_b + bs * kBBytes, &tmap, full, 0, r);
@@ -173,27 +245,30 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kStripRows, kTileCols);
+      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kMTile, kTileCols);
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const uint32_t n_btiles = items[it].n_btiles;
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_full[as]), aph);
-        const uint64_t adesc = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
+        const uint32_t n_btiles = items[it].n_btiles, m_tiles = items[it].m_tiles;
+        ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
+        const uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
         for (uint32_t t = 0; t < n_btiles; ++t) {
-          ptx::mbar_wait(ptx::smem_u32(&bars->t_empty[ts]), tph ^ 1);
-          ptx::mbar_wait(ptx::smem_u32(&bars->b_full[bs]), bph);
-          ptx::tcgen05_fence_after();
+          ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
           const uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
-          const uint32_t d = tmem_base + ts * kTileCols;
+          for (uint32_t mh = 0; mh < m_tiles; ++mh) {
+            ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
+            ptx::tcgen05_fence_after();
+            const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
+            const uint32_t d = tmem_base + ts * kTileCols;
 #pragma unroll
-          for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
-            ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
-          ptx::umma_commit(ptx::smem_u32(&bars->b_empty[bs]));
-          ptx::umma_commit(ptx::smem_u32(&bars->t_full[ts]));
+            for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
+              ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+            ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
+            if (++ts == 2) { ts = 0; tph ^= 1; }
+          }
+          ptx::umma_commit(ptx::smem_u32(&sh->b_empty[bs]));
           if (++bs == kStages) { bs = 0; bph ^= 1; }
-          if (++ts == 2) { ts = 0; tph ^= 1; }
         }
-        ptx::umma_commit(ptx::smem_u32(&bars->a_empty[as]));
+        ptx::umma_commit(ptx::smem_u32(&sh->a_empty[as]));
         if (++as == kAStages) { as = 0; aph ^= 1; }
       }
     }
@@ -205,40 +280,57 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     uint32_t ts = 0, tph = 0;
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
+      const PairMeta pm = pairs[w.pair];
+      const uint32_t strip_i0 = w.a_row - pm.a_row0 + quarter * 32 + lane;  // row index (image 1) for mh = 0
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
-        ptx::mbar_wait(ptx::smem_u32(&bars->t_full[ts]), tph);
-        ptx::tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
-        int m = 0;
+        for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
+          ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
+          ptx::tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
+          int mc[4];
 #pragma unroll
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c, v);
-          ptx::tmem_wait_ld();
-          m = max(m, max_tree(v));
-        }
-        if (__any_sync(0xffffffffu, m >= min_score)) {
-          // rare: re-read the half tile and hand every surviving entry to the accumulators
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(taddr + c, v);
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
             ptx::tmem_wait_ld();
-            if (m >= min_score) {
+            mc[c] = max_tree32(v);
+          }
+          const int m = max(max(mc[0], mc[1]), max(mc[2], mc[3]));
+          if (__any_sync(0xffffffffu, m >= min_score)) {
+            // rare: re-read only the 32-column chunks that hold a survivor and queue every survivor
+            const uint32_t i = strip_i0 + mh * kMTile;
+            const uint32_t j0 = t * kTileCols + half * 128u;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              const int mcc = c == 0 ? mc[0] : c == 1 ? mc[1] : c == 2 ? mc[2] : mc[3];  // keeps mc[] in registers
+              if (!__any_sync(0xffffffffu, mcc >= min_score)) continue;
+              uint32_t v[32];
+              ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+              ptx::tmem_wait_ld();
+              if (mcc >= min_score && i < pm.n1) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if ((int)v[e] >= min_score)
-                  emit_candidate(pairs, acc, w.pair, w.a_row, quarter * 32 + lane,
-                                 t * kTileCols + half * 128 + c + e, (int)v[e], cand_counter);
+                for (int e = 0; e < 32; ++e) {
+                  const uint32_t j = j0 + c * 32 + e;
+                  if ((int)v[e] >= min_score && j < pm.n2)
+                    queue_push(sh, pm.acc_off + i, pm.acc_off + pm.n1 + j, v[e]);
+                }
+              }
             }
           }
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
+          if (++ts == 2) { ts = 0; tph ^= 1; }
         }
-        ptx::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->t_empty[ts]));
-        if (++ts == 2) { ts = 0; tph ^= 1; }
       }
     }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      atomicAdd(&sh->q_done, 1u);
+    }
   }
+  if (warp == 2 || warp == 3) drain_loop(sh, acc, (warp - 2) * 32 + lane, cand_counter);
 
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -259,45 +351,55 @@ __global__ void __launch_bounds__(kDp4aThreads)
 score_dp4a_kernel(const uint8_t* __restrict__ pool, const WorkItem* __restrict__ items, uint32_t n_items,
                   const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
                   unsigned long long* cand_counter) {
-  __shared__ uint32_t sa[kStripRows][kDim / 4 + 1];
+  __shared__ uint32_t sa[kMTile][kDim / 4 + 1];
   __shared__ uint32_t sb[kDp4aCols][kDim / 4 + 1];
   const uint32_t tid = threadIdx.x;
   const uint32_t ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 8 rows x 4 columns each
+  unsigned long long count = 0;
   for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const WorkItem w = items[it];
-    const uint32_t* ga = reinterpret_cast<const uint32_t*>(pool + (size_t)w.a_row * kDim);
-    __syncthreads();
-    for (uint32_t x = tid; x < kStripRows * (kDim / 4); x += kDp4aThreads) sa[x >> 5][x & 31] = ga[x];
-    const uint32_t n_cols = w.n_btiles * kTileCols;
-    for (uint32_t c0 = 0; c0 < n_cols; c0 += kDp4aCols) {
-      const uint32_t* gb = reinterpret_cast<const uint32_t*>(pool + (size_t)(w.b_row + c0) * kDim);
+    const PairMeta pm = pairs[w.pair];
+    for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
+      const uint32_t a_row = w.a_row + mh * kMTile;
+      const uint32_t* ga = reinterpret_cast<const uint32_t*>(pool + (size_t)a_row * kDim);
       __syncthreads();
-      for (uint32_t x = tid; x < kDp4aCols * (kDim / 4); x += kDp4aThreads) sb[x >> 5][x & 31] = gb[x];
-      __syncthreads();
-      uint32_t s[8][4];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s[r][c] = 0;
-      for (int k = 0; k < kDim / 4; ++k) {
-        uint32_t a[8], b[4];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = sa[ty * 8 + r][k];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) b[c] = sb[tx * 4 + c][k];
+      for (uint32_t x = tid; x < kMTile * (kDim / 4); x += kDp4aThreads) sa[x >> 5][x & 31] = ga[x];
+      const uint32_t n_cols = w.n_btiles * kTileCols;
+      for (uint32_t c0 = 0; c0 < n_cols; c0 += kDp4aCols) {
+        const uint32_t* gb = reinterpret_cast<const uint32_t*>(pool + (size_t)(w.b_row + c0) * kDim);
+        __syncthreads();
+        for (uint32_t x = tid; x < kDp4aCols * (kDim / 4); x += kDp4aThreads) sb[x >> 5][x & 31] = gb[x];
+        __syncthreads();
+        uint32_t s[8][4];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) s[r][c] = __dp4a(a[r], b[c], s[r][c]);
+          for (int c = 0; c < 4; ++c) s[r][c] = 0;
+        for (int k = 0; k < kDim / 4; ++k) {
+          uint32_t a[8], b[4];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) a[r] = sa[ty * 8 + r][k];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) b[c] = sb[tx * 4 + c][k];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[r][c] = __dp4a(a[r], b[c], s[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t i = a_row - pm.a_row0 + ty * 8 + r, j = c0 + tx * 4 + c;
+            if ((int)s[r][c] >= min_score && i < pm.n1 && j < pm.n2) {
+              top2_insert2(acc, pm.acc_off + i, pm.acc_off + pm.n1 + j, s[r][c]);
+              ++count;
+            }
+          }
       }
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if ((int)s[r][c] >= min_score)
-            emit_candidate(pairs, acc, w.pair, w.a_row, ty * 8 + r, c0 + tx * 4 + c, (int)s[r][c], cand_counter);
     }
   }
+  if (cand_counter && count) atomicAdd(cand_counter, count);
 }
 
 // =====================================================================================
@@ -307,8 +409,8 @@ constexpr int kDecideThreads = 512;
 
 // acosf(min(score / 512^2, 1)) through the host-libm table; rows/columns without any surviving
 // score (k1 == 0) never match.  Returns the matched index or -1.
-__device__ __forceinline__ int decide_one(const TopTwo t, const float* __restrict__ lut, float max_ratio,
-                                          float max_distance) {
+__device__ __forceinline__ int decide_one(const TopTwo t, uint32_t base_slot, const float* __restrict__ lut,
+                                          float max_ratio, float max_distance) {
   const uint32_t best = static_cast<uint32_t>(t.k1 >> 32);
   if (best == 0) return -1;
   const uint32_t second = static_cast<uint32_t>(t.k2 >> 32);
@@ -316,7 +418,7 @@ __device__ __forceinline__ int decide_one(const TopTwo t, const float* __restric
   if (bn > max_distance) return -1;
   const float sn = __ldg(lut + min(second, (uint32_t)(kLutSize - 1)));
   if (bn >= __fmul_rn(max_ratio, sn)) return -1;  // '>=' rejects best == second-best
-  return static_cast<int>(~static_cast<uint32_t>(t.k1));
+  return static_cast<int>(~static_cast<uint32_t>(t.k1) - base_slot);
 }
 
 __global__ void __launch_bounds__(kDecideThreads)
@@ -332,7 +434,7 @@ decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, cons
 
   if (cross_check) {
     for (uint32_t j = tid; j < pm.n2; j += kDecideThreads) {
-      const int m21 = decide_one(cols[j], lut, max_ratio, max_distance);
+      const int m21 = decide_one(cols[j], pm.acc_off, lut, max_ratio, max_distance);  // keys hold row slots
       cols[j].k1 = static_cast<unsigned long long>(static_cast<uint32_t>(m21));
     }
   }
@@ -341,7 +443,7 @@ decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, cons
   // pass 1: decide every row, remember the verdict in place, count
   uint32_t cnt = 0;
   for (uint32_t i = tid; i < pm.n1; i += kDecideThreads) {
-    int m12 = decide_one(rows[i], lut, max_ratio, max_distance);
+    int m12 = decide_one(rows[i], pm.acc_off + pm.n1, lut, max_ratio, max_distance);  // keys hold column slots
     if (m12 >= 0 && cross_check && static_cast<uint32_t>(cols[m12].k1) != i) m12 = -1;
     rows[i].k1 = static_cast<unsigned long long>(static_cast<uint32_t>(m12));
     cnt += (m12 >= 0);

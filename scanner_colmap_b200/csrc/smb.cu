@@ -134,7 +134,7 @@ struct smb_handle {
 
   std::vector<smb_result*> result_pool;
   smb_timing timing{};
-  size_t acc_budget = (size_t)64 << 20;  // accumulator entries per internal batch (16 B each)
+  size_t acc_budget = (size_t)64 << 20;  // accumulator slots per internal batch (16 B each; must stay < 2^32)
 
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
@@ -224,7 +224,7 @@ int encode_tmap(smb_handle* h) {
   if (!h->pool_rows) return SMB_OK;
   cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)h->pool_rows};
   cuuint64_t gstride[1] = {(cuuint64_t)kDim};
-  cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)kStripRows};
+  cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)kMTile};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = h->encode_tiled(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->pool, gdim, gstride, box, estride,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -562,9 +562,8 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       m.n1 = a.n;
       m.b_row0 = b.row0;
       m.n2 = b.n;
-      m.acc_off = b_acc;
+      m.acc_off = (uint32_t)b_acc;
       m.out_slot = (uint32_t)p;
-      m.pad_ = 0;
       b_acc += need;
       if (a.n && b.n) b_items += (a.n + kStripRows - 1) / kStripRows;
       out_cap += cc ? std::min(a.n, b.n) : a.n;
@@ -610,7 +609,8 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       if (!m.n1 || !m.n2) continue;
       const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
       for (uint32_t r = 0; r < m.n1; r += kStripRows)
-        h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first)};
+        h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first),
+                                      m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
     }
     std::stable_sort(h->h_items.p, h->h_items.p + ni,
                      [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
