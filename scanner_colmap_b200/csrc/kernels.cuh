@@ -180,7 +180,9 @@ __device__ __forceinline__ void drain_loop(ScoreShared* sh, TopTwo* __restrict__
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
                      const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
-                     unsigned long long* cand_counter) {
+                     unsigned long long* cand_counter, uint32_t dbg) {
+  // dbg (bring-up timing experiments only, results become meaningless): 1 = epilogue releases tiles unread,
+  // 2 = B tiles are not loaded, 4 = survivors are not queued
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem0;
@@ -234,10 +236,14 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
         for (uint32_t t = 0; t < w.n_btiles; ++t) {
           ptx::mbar_wait(ptx::smem_u32(&sh->b_empty[bs]), bph ^ 1);
           const uint32_t full = ptx::smem_u32(&sh->b_full[bs]);
-          ptx::mbar_arrive_expect_tx(full, kBBytes);
-          const int32_t r = (int32_t)(w.b_row + t * kTileCols);
-          ptx::tma_load_2d(smem_b + bs * kBBytes, &tmap, full, 0, r);
-          ptx::tma_load_2d(smem_b + bs * kBBytes + kBBytes / 2, &tmap, full, 0, r + kTileCols / 2);
+          if (dbg & 2) {
+            ptx::mbar_arrive(full);
+          } else {
+            ptx::mbar_arrive_expect_tx(full, kBBytes);
+            const int32_t r = (int32_t)(w.b_row + t * kTileCols);
+            ptx::tma_load_2d(smem_b + bs * kBBytes, &tmap, full, 0, r);
+            ptx::tma_load_2d(smem_b + bs * kBBytes + kBBytes / 2, &tmap, full, 0, r + kTileCols / 2);
+          }
           if (++bs == kStages) { bs = 0; bph ^= 1; }
         }
       }
@@ -287,7 +293,8 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
-          int mc[4];
+          int mc[4] = {0, 0, 0, 0};
+          if (!(dbg & 1))
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
@@ -296,7 +303,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
             mc[c] = max_tree32(v);
           }
           const int m = max(max(mc[0], mc[1]), max(mc[2], mc[3]));
-          if (__any_sync(0xffffffffu, m >= min_score)) {
+          if (__any_sync(0xffffffffu, m >= min_score) && !(dbg & 4)) {
             // rare: re-read only the 32-column chunks that hold a survivor and queue every survivor
             const uint32_t i = strip_i0 + mh * kMTile;
             const uint32_t j0 = t * kTileCols + half * 128u;

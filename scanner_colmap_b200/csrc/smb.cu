@@ -137,6 +137,7 @@ struct smb_handle {
   size_t acc_budget = (size_t)64 << 20;  // accumulator slots per internal batch (16 B each; must stay < 2^32)
 
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+  uint32_t dbg_flags = 0;  // SMB_DEBUG_FLAGS: bring-up timing experiments (see score_tcgen05_kernel)
 };
 
 namespace {
@@ -369,6 +370,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   if (!h) return fail(nullptr, SMB_ENOMEM, "out of host memory");
   h->device = cuda_device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   int rc = SMB_OK;
   auto bail = [&](int code) {
     g_create_error = h->err;
@@ -627,7 +629,7 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
         if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
-                                                                          h->d_acc.p, h->filter.min_score, cand);
+                                                                          h->d_acc.p, h->filter.min_score, cand, h->dbg_flags);
       } else {
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
         score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p, h->d_acc.p,
