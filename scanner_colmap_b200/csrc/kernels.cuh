@@ -79,15 +79,18 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 }
 
 // =====================================================================================
-// Production score kernel: TMA -> swizzled smem -> tcgen05.mma kind::i8 -> TMEM -> filter
+// Production score kernel: TMA -> swizzled smem -> tcgen05.mma kind::i8 -> TMEM -> filter -> rescore
 //
-//   warp 0      TMA producer: A strip (256 rows, kept for the whole item) + ring of B tiles (256 rows)
-//   warp 1      MMA issuer: per B tile two accumulator tiles (strip rows 0-127 / 128-255), 4 x K32 each,
-//               ping-pong between the two 256-column halves of TMEM
-//   warp 2      TMEM allocator, then candidate drain
-//   warp 3      candidate drain: pops the shared-memory queue and feeds the top-2 accumulators (global
-//               atomics) so their latency never sits in the tile pipeline
-//   warps 4-11  filter epilogue: tcgen05.ld + 3-input max tree; entries >= min_score -> queue
+//   warp 0        TMA producer: A strip (256 rows, kept for the whole item) + ring of B tiles (256 rows)
+//   warp 1        MMA issuer: per B tile two accumulator tiles (strip rows 0-127 / 128-255), 4 x K32 each,
+//                 ping-pong between the two 256-column halves of TMEM
+//   warps 4-11    filter epilogue: tcgen05.ld + 3-input max tree over each thread's 32-column run; the
+//                 accumulator buffer is released as soon as it has been read.  A run whose maximum
+//                 reaches min_score is not re-read: its (row, 32-column run) address goes to a
+//                 shared-memory queue.
+//   warps 2,3,12-15  rescoring: pop a (row, run), recompute its 32 dot products exactly on CUDA cores
+//                 (__dp4a over the descriptors in L2) and feed every score >= min_score to the top-2
+//                 accumulators (global atomics).  All of that latency is off the tile pipeline.
 // =====================================================================================
 constexpr int kStages = 4;                     // B-tile ring
 constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
@@ -95,14 +98,11 @@ constexpr int kMTile = 128;                    // UMMA M
 constexpr int kABytes = kStripRows * kDim;     // 32 KiB (two 128-row boxes)
 constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
 constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter
-constexpr int kDrainWarps = 2;
-constexpr int kScoreThreads = 32 * (4 + kEpiWarps);
-constexpr int kQueueSlots = 1024;              // candidate queue entries (16 B each)
-
-struct Cand {
-  uint32_t row_slot, col_slot, score;
-  uint32_t flag;  // 2g = free for generation g, 2g+1 = holds the entry of generation g
-};
+constexpr int kRescoreWarps = 6;
+constexpr int kScoreWarps = 16;
+constexpr int kScoreThreads = 32 * kScoreWarps;
+constexpr int kQueueSlots = 1024;              // (row, run) queue entries
+constexpr int kRunCols = 32;                   // columns per thread per tcgen05.ld == rescoring granularity
 
 struct ScoreShared {
   uint64_t a_full[kAStages], a_empty[kAStages];
@@ -112,9 +112,12 @@ struct ScoreShared {
   uint32_t q_tail;      // next queue slot to claim
   uint32_t q_done;      // epilogue warps that have finished
   uint32_t pad_;
-  Cand queue[kQueueSlots];
+  uint4 q_entry[kQueueSlots];    // {pool row of the image-1 descriptor, pool row of the run's first image-2
+                                 //  descriptor, accumulator slot of the row, accumulator slot of the run's first column}
+  uint32_t q_flag[kQueueSlots];  // 2g = free for generation g, 2g+1 = holds the entry of generation g
 };
 constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + (int)sizeof(ScoreShared);
+static_assert(kScoreSmemBytes <= 227 * 1024, "shared memory budget");
 
 // max over 32 accumulator entries with 3-input integer max (VIMNMX3), as a tree for ILP:
 // 16 instructions per 32 entries
@@ -130,59 +133,83 @@ __device__ __forceinline__ int max_tree32(const uint32_t (&v)[32]) {
   return max(__vimax3_s32(b0, b1, b2), b3);
 }
 
-__device__ __forceinline__ void queue_push(ScoreShared* sh, uint32_t row_slot, uint32_t col_slot, uint32_t score) {
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+__device__ __forceinline__ void queue_push(ScoreShared* sh, uint4 entry) {
   const uint32_t s = atomicAdd(&sh->q_tail, 1u);
-  Cand* c = &sh->queue[s % kQueueSlots];
+  const uint32_t slot = s % kQueueSlots;
   const uint32_t gen2 = (s / kQueueSlots) * 2;
-  volatile uint32_t* flag = &c->flag;
+  volatile uint32_t* flag = &sh->q_flag[slot];
   uint32_t spins = 0;
-  while (*flag != gen2) {  // previous occupant not drained yet (queue full): back-pressure
+  while (*flag != gen2) {  // previous occupant not consumed yet (queue full): back-pressure
     if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
   }
-  c->row_slot = row_slot;
-  c->col_slot = col_slot;
-  c->score = score;
-  __threadfence_block();
+  sh->q_entry[slot] = entry;
+  fence_cta();
   *flag = gen2 + 1;
 }
 
-__device__ __forceinline__ void drain_loop(ScoreShared* sh, TopTwo* __restrict__ acc, uint32_t drain_lane,
-                                           unsigned long long* cand_counter) {
-  uint32_t idx = drain_lane;  // this lane owns queue slots idx, idx + 32*kDrainWarps, ...
+// One rescoring warp: owns queue slots r, r + kRescoreWarps, ...; lane l recomputes column (run + l).
+__device__ __forceinline__ void rescore_loop(ScoreShared* sh, const uint8_t* __restrict__ pool, TopTwo* __restrict__ acc,
+                                             int min_score, uint32_t r, uint32_t lane, unsigned long long* cand_counter) {
+  uint32_t idx = r;
   uint32_t count = 0;
   volatile uint32_t* tail = &sh->q_tail;
   volatile uint32_t* done = &sh->q_done;
   for (;;) {
-    Cand* c = &sh->queue[idx % kQueueSlots];
-    volatile uint32_t* flag = &c->flag;
+    const uint32_t slot = idx % kQueueSlots;
+    volatile uint32_t* flag = &sh->q_flag[slot];
     const uint32_t want = (idx / kQueueSlots) * 2 + 1;
-    bool got = false;
-    if (*flag == want) {
-      __threadfence_block();
-      const uint32_t r = *(volatile uint32_t*)&c->row_slot;
-      const uint32_t cs = *(volatile uint32_t*)&c->col_slot;
-      const uint32_t sc = *(volatile uint32_t*)&c->score;
-      __threadfence_block();
-      *flag = want + 1;  // free for the next generation
-      top2_insert2(acc, r, cs, sc);
-      idx += 32 * kDrainWarps;
-      ++count;
-      got = true;
-    } else if (*done == kEpiWarps) {
-      __threadfence_block();
-      if (idx >= *tail) break;  // q_done is bumped only after every push of that warp is visible
+    if (*flag == want) {  // same address for every lane: warp-uniform
+      fence_cta();
+      uint4 e;
+      asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                   : "r"(ptx::smem_u32(&sh->q_entry[slot]))
+                   : "memory");
+      __syncwarp();
+      if (lane == 0) *flag = want + 1;  // free for the next generation
+      const uint4* pa = reinterpret_cast<const uint4*>(pool + (size_t)e.x * kDim);
+      const uint4* pb = reinterpret_cast<const uint4*>(pool + (size_t)(e.y + lane) * kDim);
+      uint32_t sc = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // two batches of 4 x 16 B per operand keep the register footprint small
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[k] = __ldg(pa + h * 4 + k);
+          b[k] = __ldg(pb + h * 4 + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sc = __dp4a(a[k].x, b[k].x, sc);
+          sc = __dp4a(a[k].y, b[k].y, sc);
+          sc = __dp4a(a[k].z, b[k].z, sc);
+          sc = __dp4a(a[k].w, b[k].w, sc);
+        }
+      }
+      if ((int)sc >= min_score) {  // pool padding rows are zero and can never get here
+        top2_insert2(acc, e.z, e.w + lane, sc);
+        ++count;
+      }
+      idx += kRescoreWarps;
+    } else {
+      if (*done == kEpiWarps) {
+        fence_cta();
+        if (idx >= *tail) break;  // q_done is bumped only after every push of that warp is visible
+      }
+      __nanosleep(64);
     }
-    if (!got) __nanosleep(128);
   }
   if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
 }
 
 __global__ void __launch_bounds__(kScoreThreads, 1)
-score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
-                     const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
-                     unsigned long long* cand_counter, uint32_t dbg) {
+score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ pool,
+                     const WorkItem* __restrict__ items, uint32_t n_items, const PairMeta* __restrict__ pairs,
+                     TopTwo* __restrict__ acc, int min_score, unsigned long long* cand_counter, uint32_t dbg) {
   // dbg (bring-up timing experiments only, results become meaningless): 1 = epilogue releases tiles unread,
-  // 2 = B tiles are not loaded, 4 = survivors are not queued
+  // 2 = B tiles are not loaded, 4 = hits are not queued
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem0;
@@ -211,7 +238,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     sh->q_done = 0;
     ptx::fence_barrier_init();
   }
-  for (uint32_t x = threadIdx.x; x < kQueueSlots; x += kScoreThreads) sh->queue[x].flag = 0;
+  for (uint32_t x = threadIdx.x; x < kQueueSlots; x += kScoreThreads) sh->q_flag[x] = 0;
   if (warp == 2) {  // whole warp: TMEM allocation (all 512 columns: two 256-column accumulators)
     ptx::tmem_alloc_512(ptx::smem_u32(&sh->tmem_base));
     ptx::tmem_relinquish();
@@ -278,7 +305,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
         if (++as == kAStages) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ------------------------------------------------------------ filter epilogue (8 warps)
     const uint32_t quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are visible to this warp
     const uint32_t half = (warp - 4) >> 2;        // which 128 of the tile's 256 columns
@@ -287,57 +314,51 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairMeta pm = pairs[w.pair];
-      const uint32_t strip_i0 = w.a_row - pm.a_row0 + quarter * 32 + lane;  // row index (image 1) for mh = 0
+      const uint32_t a_row = w.a_row + quarter * 32 + lane;              // pool row of this thread's descriptor (mh = 0)
+      const uint32_t row_slot = pm.acc_off + (a_row - pm.a_row0);        // its accumulator slot
+      const uint32_t col_slot0 = pm.acc_off + pm.n1 + half * 128u;
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
           int mc[4] = {0, 0, 0, 0};
-          if (!(dbg & 1))
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-            ptx::tmem_wait_ld();
-            mc[c] = max_tree32(v);
-          }
-          const int m = max(max(mc[0], mc[1]), max(mc[2], mc[3]));
-          if (__any_sync(0xffffffffu, m >= min_score) && !(dbg & 4)) {
-            // rare: re-read only the 32-column chunks that hold a survivor and queue every survivor
-            const uint32_t i = strip_i0 + mh * kMTile;
-            const uint32_t j0 = t * kTileCols + half * 128u;
-#pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-              const int mcc = c == 0 ? mc[0] : c == 1 ? mc[1] : c == 2 ? mc[2] : mc[3];  // keeps mc[] in registers
-              if (!__any_sync(0xffffffffu, mcc >= min_score)) continue;
               uint32_t v[32];
-              ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+              ptx::tmem_ld_32x32b_x32(taddr + c * kRunCols, v);
               ptx::tmem_wait_ld();
-              if (mcc >= min_score && i < pm.n1) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  const uint32_t j = j0 + c * 32 + e;
-                  if ((int)v[e] >= min_score && j < pm.n2)
-                    queue_push(sh, pm.acc_off + i, pm.acc_off + pm.n1 + j, v[e]);
-                }
-              }
+              mc[c] = max_tree32(v);
             }
           }
+          // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp
           ptx::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
+          const int m = max(max(mc[0], mc[1]), max(mc[2], mc[3]));
+          if (__any_sync(0xffffffffu, m >= min_score) && !(dbg & 4)) {
+            const uint32_t j0 = t * kTileCols + half * 128u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (mc[c] >= min_score)
+                queue_push(sh, make_uint4(a_row + mh * kMTile, w.b_row + j0 + c * kRunCols, row_slot + mh * kMTile,
+                                          col_slot0 + t * kTileCols + c * kRunCols));
+          }
         }
       }
     }
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();
+      fence_cta();
       atomicAdd(&sh->q_done, 1u);
     }
+  } else {
+    // ------------------------------------------------------------ rescoring (warps 2, 3, 12-15)
+    const uint32_t r = warp < 4 ? warp - 2 : warp - 10;
+    rescore_loop(sh, pool, acc, min_score, r, lane, cand_counter);
   }
-  if (warp == 2 || warp == 3) drain_loop(sh, acc, (warp - 2) * 32 + lane, cand_counter);
 
   ptx::tcgen05_fence_before();
   __syncthreads();

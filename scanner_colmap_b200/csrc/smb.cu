@@ -628,7 +628,7 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       if (h->opts.engine == SMB_ENGINE_TCGEN05) {
         if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);
-        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
+        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
                                                                           h->d_acc.p, h->filter.min_score, cand, h->dbg_flags);
       } else {
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
