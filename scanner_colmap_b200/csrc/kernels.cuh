@@ -88,35 +88,38 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 //                 accumulator buffer is released as soon as it has been read.  A run whose maximum
 //                 reaches min_score is not re-read: its (row, 32-column run) address goes to a
 //                 shared-memory queue.
-//   warps 2,3,12-15  rescoring: pop a (row, run), recompute its 32 dot products exactly on CUDA cores
-//                 (__dp4a over the descriptors in L2) and feed every score >= min_score to the top-2
-//                 accumulators (global atomics).  All of that latency is off the tile pipeline.
+//   warps 2,3,12,13  rescoring: pop up to 4 (row, run) entries at a time, recompute their 32 dot products
+//                 exactly on CUDA cores (__dp4a over the descriptors in L2) and feed every score
+//                 >= min_score to the top-2 accumulators (global atomics).  All of that latency is off
+//                 the tile pipeline.
 // =====================================================================================
-constexpr int kStages = 4;                     // B-tile ring
+constexpr int kStages = 3;                     // B-tile ring
 constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
 constexpr int kMTile = 128;                    // UMMA M
 constexpr int kABytes = kStripRows * kDim;     // 32 KiB (two 128-row boxes)
 constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
 constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter
-constexpr int kRescoreWarps = 6;
-constexpr int kScoreWarps = 16;
+constexpr int kRescoreWarps = 4;               // warps 2, 3, 12, 13
+constexpr int kScoreWarps = 4 + kEpiWarps + 2;
 constexpr int kScoreThreads = 32 * kScoreWarps;
-constexpr int kQueueSlots = 1024;              // (row, run) queue entries
 constexpr int kRunCols = 32;                   // columns per thread per tcgen05.ld == rescoring granularity
+constexpr int kHitSlots = 12;                  // staging ring for (row, run) hits
+constexpr int kHitBytes = kDim + kRunCols * kDim;  // one image-1 descriptor + 32 image-2 descriptors
 
 struct ScoreShared {
   uint64_t a_full[kAStages], a_empty[kAStages];
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t t_full[2], t_empty[2];
+  uint64_t h_full[kHitSlots];      // hit staging: descriptors of the hit have landed (tx-count barrier)
+  uint32_t h_free_gen[kHitSlots];  // generation that may next write the slot
+  uint2 h_meta[kHitSlots];         // {accumulator slot of the row, accumulator slot of the run's first column}
+  uint32_t h_tail;                 // next hit sequence number
+  uint32_t h_done;                 // epilogue warps that have finished
   uint32_t tmem_base;
-  uint32_t q_tail;      // next queue slot to claim
-  uint32_t q_done;      // epilogue warps that have finished
   uint32_t pad_;
-  uint4 q_entry[kQueueSlots];    // {pool row of the image-1 descriptor, pool row of the run's first image-2
-                                 //  descriptor, accumulator slot of the row, accumulator slot of the run's first column}
-  uint32_t q_flag[kQueueSlots];  // 2g = free for generation g, 2g+1 = holds the entry of generation g
 };
-constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + (int)sizeof(ScoreShared);
+constexpr int kScoreSmemBytes =
+    1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + kHitSlots * kHitBytes + (int)sizeof(ScoreShared);
 static_assert(kScoreSmemBytes <= 227 * 1024, "shared memory budget");
 
 // max over 32 accumulator entries with 3-input integer max (VIMNMX3), as a tree for ILP:
@@ -135,74 +138,79 @@ __device__ __forceinline__ int max_tree32(const uint32_t (&v)[32]) {
 
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
-__device__ __forceinline__ void queue_push(ScoreShared* sh, uint4 entry) {
-  const uint32_t s = atomicAdd(&sh->q_tail, 1u);
-  const uint32_t slot = s % kQueueSlots;
-  const uint32_t gen2 = (s / kQueueSlots) * 2;
-  volatile uint32_t* flag = &sh->q_flag[slot];
+// Epilogue side: a (row, 32-column run) whose maximum reached min_score.  Claim a staging slot and let
+// the bulk-copy engine fetch the 1 + 32 descriptors involved (L2 -> shared memory); the rescoring warps
+// pick the slot up when its barrier completes.  Nothing here waits on memory.
+__device__ __forceinline__ void hit_push(ScoreShared* sh, uint32_t smem_hits, const uint8_t* __restrict__ pool,
+                                         uint32_t a_row, uint32_t b_row, uint32_t row_slot, uint32_t col_slot0) {
+  const uint32_t s = atomicAdd(&sh->h_tail, 1u);
+  const uint32_t slot = s % kHitSlots, gen = s / kHitSlots;
+  volatile uint32_t* free_gen = &sh->h_free_gen[slot];
   uint32_t spins = 0;
-  while (*flag != gen2) {  // previous occupant not consumed yet (queue full): back-pressure
+  while (*free_gen != gen) {  // ring full: back-pressure until the rescoring warps catch up
     if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
   }
-  sh->q_entry[slot] = entry;
-  fence_cta();
-  *flag = gen2 + 1;
+  sh->h_meta[slot] = make_uint2(row_slot, col_slot0);
+  const uint32_t bar = ptx::smem_u32(&sh->h_full[slot]);
+  const uint32_t dst = smem_hits + slot * kHitBytes;
+  ptx::mbar_arrive_expect_tx(bar, kHitBytes);  // release: the meta store is visible to whoever sees the phase flip
+  ptx::bulk_load(dst, pool + (size_t)a_row * kDim, kDim, bar);
+  ptx::bulk_load(dst + kDim, pool + (size_t)b_row * kDim, kRunCols * kDim, bar);
 }
 
-// One rescoring warp: owns queue slots r, r + kRescoreWarps, ...; lane l recomputes column (run + l).
-__device__ __forceinline__ void rescore_loop(ScoreShared* sh, const uint8_t* __restrict__ pool, TopTwo* __restrict__ acc,
-                                             int min_score, uint32_t r, uint32_t lane, unsigned long long* cand_counter) {
-  uint32_t idx = r;
-  uint32_t count = 0;
-  volatile uint32_t* tail = &sh->q_tail;
-  volatile uint32_t* done = &sh->q_done;
+// Rescoring warp r owns hit sequence numbers r, r + kRescoreWarps, ...  Lane l recomputes the exact score
+// of column (run + l) from the staged descriptors (bank-conflict-free rotation); scores >= min_score go to
+// the top-2 accumulators.
+__device__ __forceinline__ void rescore_loop(ScoreShared* sh, uint32_t smem_hits, TopTwo* __restrict__ acc, int min_score,
+                                             uint32_t r, uint32_t lane, unsigned long long* cand_counter) {
+  uint32_t n = r, count = 0;
+  volatile uint32_t* tail = &sh->h_tail;
+  volatile uint32_t* done = &sh->h_done;
   for (;;) {
-    const uint32_t slot = idx % kQueueSlots;
-    volatile uint32_t* flag = &sh->q_flag[slot];
-    const uint32_t want = (idx / kQueueSlots) * 2 + 1;
-    if (*flag == want) {  // same address for every lane: warp-uniform
-      fence_cta();
-      uint4 e;
-      asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
-                   : "r"(ptx::smem_u32(&sh->q_entry[slot]))
-                   : "memory");
-      __syncwarp();
-      if (lane == 0) *flag = want + 1;  // free for the next generation
-      const uint4* pa = reinterpret_cast<const uint4*>(pool + (size_t)e.x * kDim);
-      const uint4* pb = reinterpret_cast<const uint4*>(pool + (size_t)(e.y + lane) * kDim);
-      uint32_t sc = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {  // two batches of 4 x 16 B per operand keep the register footprint small
-        uint4 a[4], b[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          a[k] = __ldg(pa + h * 4 + k);
-          b[k] = __ldg(pb + h * 4 + k);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sc = __dp4a(a[k].x, b[k].x, sc);
-          sc = __dp4a(a[k].y, b[k].y, sc);
-          sc = __dp4a(a[k].z, b[k].z, sc);
-          sc = __dp4a(a[k].w, b[k].w, sc);
-        }
-      }
-      if ((int)sc >= min_score) {  // pool padding rows are zero and can never get here
-        top2_insert2(acc, e.z, e.w + lane, sc);
-        ++count;
-      }
-      idx += kRescoreWarps;
-    } else {
+    const uint32_t slot = n % kHitSlots, gen = n / kHitSlots;
+    const uint32_t bar = ptx::smem_u32(&sh->h_full[slot]);
+    bool finished = false;
+    while (!ptx::mbar_try_wait(bar, gen & 1)) {
       if (*done == kEpiWarps) {
         fence_cta();
-        if (idx >= *tail) break;  // q_done is bumped only after every push of that warp is visible
+        if (n >= *tail) {  // h_done is bumped only after every push of that warp is visible
+          finished = true;
+          break;
+        }
       }
-      __nanosleep(64);
+      __nanosleep(128);
     }
+    if (finished) break;
+    uint2 meta;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(meta.x), "=r"(meta.y)
+                 : "r"(ptx::smem_u32(&sh->h_meta[slot]))
+                 : "memory");
+    const uint32_t base = smem_hits + slot * kHitBytes;
+    uint32_t sc = 0;
+#pragma unroll
+    for (int k = 0; k < kDim / 4; ++k) {
+      const uint32_t w = (lane + k) & 31;  // rotation: every lane touches a different bank in each step
+      uint32_t av, bv;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(av) : "r"(base + w * 4));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bv) : "r"(base + kDim + lane * kDim + w * 4));
+      sc = __dp4a(av, bv, sc);
+    }
+    __syncwarp();
+    if (lane == 0) sh->h_free_gen[slot] = gen + 1;  // slot may be refilled
+    if ((int)sc >= min_score) {  // pool padding rows are zero and can never get here
+      top2_insert2(acc, meta.x, meta.y + lane, sc);
+      ++count;
+    }
+    n += kRescoreWarps;
   }
   if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
 }
+
+// Bring-up instrumentation (dbg & 32): per-CTA cycle totals, [cta][16]:
+// 0 mma: wait b_full, 1 mma: wait t_empty, 2 mma: total, 3 mma: tiles,
+// 4 epi(warp 4): wait t_full, 5 epi: ld+max, 6 epi: push, 7 epi: total, 8 prod: wait b_empty, 9 prod: total
+__device__ long long g_score_clocks[148 * 16];
 
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ pool,
@@ -214,8 +222,9 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem0;
   const uint32_t smem_b = smem0 + kAStages * kABytes;
-  ScoreShared* sh =
-      reinterpret_cast<ScoreShared*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes + kStages * kBBytes);
+  const uint32_t smem_hits = smem_b + kStages * kBBytes;
+  ScoreShared* sh = reinterpret_cast<ScoreShared*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes +
+                                                   kStages * kBBytes + kHitSlots * kHitBytes);
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
@@ -234,11 +243,14 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
       ptx::mbar_init(ptx::smem_u32(&sh->t_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), kEpiWarps);
     }
-    sh->q_tail = 0;
-    sh->q_done = 0;
+    for (int s = 0; s < kHitSlots; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&sh->h_full[s]), 1);
+      sh->h_free_gen[s] = 0;
+    }
+    sh->h_tail = 0;
+    sh->h_done = 0;
     ptx::fence_barrier_init();
   }
-  for (uint32_t x = threadIdx.x; x < kQueueSlots; x += kScoreThreads) sh->q_flag[x] = 0;
   if (warp == 2) {  // whole warp: TMEM allocation (all 512 columns: two 256-column accumulators)
     ptx::tmem_alloc_512(ptx::smem_u32(&sh->tmem_base));
     ptx::tmem_relinquish();
@@ -252,6 +264,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
     // ------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      long long c_wait = 0, c_t0 = clock64();
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
         ptx::mbar_wait(ptx::smem_u32(&sh->a_empty[as]), aph ^ 1);
@@ -261,7 +274,9 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
           ptx::tma_load_2d(smem_a + as * kABytes + mh * (kABytes / 2), &tmap, afull, 0, (int32_t)(w.a_row + mh * kMTile));
         if (++as == kAStages) { as = 0; aph ^= 1; }
         for (uint32_t t = 0; t < w.n_btiles; ++t) {
+          const long long c0 = (dbg & 32) ? clock64() : 0;
           ptx::mbar_wait(ptx::smem_u32(&sh->b_empty[bs]), bph ^ 1);
+          if (dbg & 32) c_wait += clock64() - c0;
           const uint32_t full = ptx::smem_u32(&sh->b_full[bs]);
           if (dbg & 2) {
             ptx::mbar_arrive(full);
@@ -274,21 +289,30 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
           if (++bs == kStages) { bs = 0; bph ^= 1; }
         }
       }
+      if ((dbg & 32) && blockIdx.x < 148) {
+        g_score_clocks[blockIdx.x * 16 + 8] = c_wait;
+        g_score_clocks[blockIdx.x * 16 + 9] = clock64() - c_t0;
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kMTile, kTileCols);
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
+      long long c_b = 0, c_t = 0, c_n = 0, c_t0 = clock64();
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const uint32_t n_btiles = items[it].n_btiles, m_tiles = items[it].m_tiles;
         ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
         const uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
         for (uint32_t t = 0; t < n_btiles; ++t) {
+          long long c0 = (dbg & 32) ? clock64() : 0;
           ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
+          if (dbg & 32) c_b += clock64() - c0;
           const uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
           for (uint32_t mh = 0; mh < m_tiles; ++mh) {
+            c0 = (dbg & 32) ? clock64() : 0;
             ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
+            if (dbg & 32) { c_t += clock64() - c0; ++c_n; }
             ptx::tcgen05_fence_after();
             const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
             const uint32_t d = tmem_base + ts * kTileCols;
@@ -304,6 +328,12 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
         ptx::umma_commit(ptx::smem_u32(&sh->a_empty[as]));
         if (++as == kAStages) { as = 0; aph ^= 1; }
       }
+      if ((dbg & 32) && blockIdx.x < 148) {
+        g_score_clocks[blockIdx.x * 16 + 0] = c_b;
+        g_score_clocks[blockIdx.x * 16 + 1] = c_t;
+        g_score_clocks[blockIdx.x * 16 + 2] = clock64() - c_t0;
+        g_score_clocks[blockIdx.x * 16 + 3] = c_n;
+      }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ------------------------------------------------------------ filter epilogue (8 warps)
@@ -311,6 +341,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
     const uint32_t half = (warp - 4) >> 2;        // which 128 of the tile's 256 columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
     uint32_t ts = 0, tph = 0;
+    long long c_w = 0, c_l = 0, c_p = 0, c_t0 = clock64();
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairMeta pm = pairs[w.pair];
@@ -319,18 +350,23 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
       const uint32_t col_slot0 = pm.acc_off + pm.n1 + half * 128u;
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
+          long long c0 = (dbg & 32) ? clock64() : 0;
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
+          long long c1 = (dbg & 32) ? clock64() : 0;
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + half * 128u;
           int mc[4] = {0, 0, 0, 0};
           if (!(dbg & 1)) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              ptx::tmem_ld_32x32b_x32(taddr + c * kRunCols, v);
-              ptx::tmem_wait_ld();
-              mc[c] = max_tree32(v);
-            }
+            uint32_t v0[32], v1[32], v2[32], v3[32];  // all four runs in flight; ptxas tracks each load's registers
+            ptx::tmem_ld_32x32b_x32(taddr, v0);
+            ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
+            ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
+            ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
+            ptx::tmem_wait_ld();
+            mc[0] = max_tree32(v0);
+            mc[1] = max_tree32(v1);
+            mc[2] = max_tree32(v2);
+            mc[3] = max_tree32(v3);
           }
           // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp
           ptx::tcgen05_fence_before();
@@ -338,26 +374,33 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
           const int m = max(max(mc[0], mc[1]), max(mc[2], mc[3]));
+          long long c2 = (dbg & 32) ? clock64() + (m & 0) : 0;
           if (__any_sync(0xffffffffu, m >= min_score) && !(dbg & 4)) {
             const uint32_t j0 = t * kTileCols + half * 128u;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               if (mc[c] >= min_score)
-                queue_push(sh, make_uint4(a_row + mh * kMTile, w.b_row + j0 + c * kRunCols, row_slot + mh * kMTile,
-                                          col_slot0 + t * kTileCols + c * kRunCols));
+                hit_push(sh, smem_hits, pool, a_row + mh * kMTile, w.b_row + j0 + c * kRunCols, row_slot + mh * kMTile,
+                         col_slot0 + t * kTileCols + c * kRunCols);
           }
+          if (dbg & 32) { c_w += c1 - c0; c_l += c2 - c1; c_p += clock64() - c2; }
         }
       }
     }
     __syncwarp();
+    if ((dbg & 32) && warp == 4 && lane == 0 && blockIdx.x < 148) {
+      g_score_clocks[blockIdx.x * 16 + 4] = c_w;
+      g_score_clocks[blockIdx.x * 16 + 5] = c_l;
+      g_score_clocks[blockIdx.x * 16 + 6] = c_p;
+      g_score_clocks[blockIdx.x * 16 + 7] = clock64() - c_t0;
+    }
     if (lane == 0) {
       fence_cta();
-      atomicAdd(&sh->q_done, 1u);
+      atomicAdd(&sh->h_done, 1u);
     }
   } else {
-    // ------------------------------------------------------------ rescoring (warps 2, 3, 12-15)
-    const uint32_t r = warp < 4 ? warp - 2 : warp - 10;
-    rescore_loop(sh, pool, acc, min_score, r, lane, cand_counter);
+    // ------------------------------------------------------------ rescoring (warps 2, 3, 12, 13)
+    rescore_loop(sh, smem_hits, acc, min_score, warp < 4 ? warp - 2 : warp - 10, lane, cand_counter);
   }
 
   ptx::tcgen05_fence_before();

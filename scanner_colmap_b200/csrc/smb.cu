@@ -765,6 +765,14 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
   return rc;
 }
 
+/* Bring-up only (not in smb.h): copies the score kernel's cycle counters (SMB_DEBUG_FLAGS & 32). */
+int smb_debug_clocks(smb_handle* h, long long* out, size_t n) {
+  if (!h || !out) return SMB_EINVAL;
+  if (n > 148 * 16) n = 148 * 16;
+  SMB_CUDA(h, cudaMemcpyFromSymbol(out, smb::g_score_clocks, n * sizeof(long long)));
+  return SMB_OK;
+}
+
 int smb_get_timing(const smb_handle* h, smb_timing* t) {
   if (!h || !t) return SMB_EINVAL;
   *t = h->timing;
