@@ -612,7 +612,7 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
       for (uint32_t r = 0; r < m.n1; r += kStripRows)
         h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first),
-                                      m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
+                                      m.n1 - r > 2u * (uint32_t)kMTile ? 2u : 1u};
     }
     std::stable_sort(h->h_items.p, h->h_items.p + ni,
                      [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
@@ -627,7 +627,8 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
       if (h->opts.engine == SMB_ENGINE_TCGEN05) {
         if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
-        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);
+        // one CTA pair (cluster of 2) per work item, persistent over the item list
+        const unsigned grid = 2u * (unsigned)std::min<size_t>(ni, (size_t)h->num_sms / 2);
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
                                                                           h->d_acc.p, h->filter.min_score, cand, h->dbg_flags);
       } else {
@@ -763,14 +764,6 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
     }
   }
   return rc;
-}
-
-/* Bring-up only (not in smb.h): copies the score kernel's cycle counters (SMB_DEBUG_FLAGS & 32). */
-int smb_debug_clocks(smb_handle* h, long long* out, size_t n) {
-  if (!h || !out) return SMB_EINVAL;
-  if (n > 148 * 16) n = 148 * 16;
-  SMB_CUDA(h, cudaMemcpyFromSymbol(out, smb::g_score_clocks, n * sizeof(long long)));
-  return SMB_OK;
 }
 
 int smb_get_timing(const smb_handle* h, smb_timing* t) {

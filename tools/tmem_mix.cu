@@ -27,7 +27,7 @@ __device__ __forceinline__ void ld_16x256b_x8(uint32_t taddr) {  // 16 lanes x 2
 }
 
 // mode: 0 = x32, 1 = x64, 2 = 16x256b.x8
-__global__ void __launch_bounds__(384, 1) mix_kernel(int mma_iters, int ld_iters, int n_ld_warps, int mode, int waits_every,
+__global__ void __launch_bounds__(640, 1) mix_kernel(int mma_iters, int ld_iters, int n_ld_warps, int mode, int waits_every,
                                                       long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(384, 1) mix_kernel(int mma_iters, int ld_iters
   }
   if (warp >= 4 && warp < 4 + n_ld_warps && ld_iters > 0) {
     const uint32_t lane_addr = ((warp & 3) * 32u) << 16;
-    const uint32_t colbase = 256 + ((warp - 4) >> 2) * 128;    // columns 256..511: the "other" accumulator
+    const uint32_t colbase = 256 + (((warp - 4) >> 2) & 1) * 128;    // columns 256..511: the "other" accumulator
     long long t0 = clock64();
     for (int i = 0; i < ld_iters; ++i) {
       const uint32_t ta = tb + lane_addr + colbase + (i & 1) * 64;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(384, 1) mix_kernel(int mma_iters, int ld_iters
       if ((i + 1) % waits_every == 0) tmem_wait_ld();
     }
     tmem_wait_ld();
-    out[blockIdx.x * 16 + warp] = clock64() - t0;
+    if (warp < 16) out[blockIdx.x * 16 + warp] = clock64() - t0;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -82,6 +82,8 @@ int main() {
   const int mma_iters = 1000, ld_iters = 4000;
   struct Cfg { int mma, ld, warps, mode, waits; const char* name; } cfgs[] = {
     {0, 1, 4, 0, 1, "ld x32 x2, 4 warps, wait each"}, {0, 1, 8, 0, 1, "ld x32 x2, 8 warps, wait each"},
+    {0, 1, 12, 0, 1, "ld x32 x2, 12 warps, wait each"}, {0, 1, 16, 0, 1, "ld x32 x2, 16 warps, wait each"},
+    {1, 1, 16, 0, 1, "mma + ld x32x2 16 warps"}, {1, 1, 12, 0, 1, "mma + ld x32x2 12 warps"},
     {0, 1, 4, 0, 4, "ld x32 x2, 4 warps, wait/4"},   {0, 1, 8, 0, 4, "ld x32 x2, 8 warps, wait/4"},
     {0, 1, 4, 1, 1, "ld x64, 4 warps, wait each"},   {0, 1, 8, 1, 1, "ld x64, 8 warps, wait each"},
     {0, 1, 8, 2, 1, "ld 16x256b.x8 x2, 8 warps"},
@@ -93,12 +95,12 @@ int main() {
     cudaMemset(d, 0, sms * 16 * sizeof(long long));
     // size the ld loop so both roles run for a similar time when mixed
     for (int rep = 0; rep < 2; ++rep)
-      mix_kernel<<<sms, 384, smem>>>(c.mma ? mma_iters : 0, c.ld ? ld_iters : 0, c.warps, c.mode, c.waits, d);
+      mix_kernel<<<sms, 640, smem>>>(c.mma ? mma_iters : 0, c.ld ? ld_iters : 0, c.warps, c.mode, c.waits, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: ERROR %s\n", c.name, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d, sms * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
     long long mma_c = 0, ld_c = 0;
-    for (int b = 0; b < sms; ++b) { mma_c = h[b*16] > mma_c ? h[b*16] : mma_c; for (int w = 4; w < 12; ++w) ld_c = h[b*16+w] > ld_c ? h[b*16+w] : ld_c; }
+    for (int b = 0; b < sms; ++b) { mma_c = h[b*16] > mma_c ? h[b*16] : mma_c; for (int w = 4; w < 16; ++w) ld_c = h[b*16+w] > ld_c ? h[b*16+w] : ld_c; }
     printf("%-34s", c.name);
     if (c.mma) printf(" mma: %7.1f cyc/MMA (128 ideal)", (double)mma_c / (mma_iters * 4.0));
     if (c.ld) printf("  ld: %7.1f cyc per 64 cols per warp -> %6.1f B/clk/SM", (double)ld_c / ld_iters,
