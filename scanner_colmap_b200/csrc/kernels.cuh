@@ -23,7 +23,7 @@
 namespace smb {
 
 constexpr int kDim = 128;            // descriptor bytes == GEMM K
-constexpr int kStripRows = 512;      // rows of image 1 per work item: a CTA pair (M = 256) x up to two row blocks
+constexpr int kStripRows = 256;      // rows of image 1 per work item (two UMMA M=128 row blocks)
 constexpr int kTileCols = 256;       // columns (rows of image 2) per accumulator tile == UMMA N
 constexpr int kRowPad = 256;         // every cached image occupies a multiple of this many pool rows
 constexpr int kLutSize = 512 * 512 + 1;
@@ -37,12 +37,12 @@ struct PairMeta {
   uint32_t out_slot; // index into the per-call pair_out array
 };
 
-struct WorkItem {     // one strip (<= 512 rows) of image 1 against all of image 2, processed by one CTA pair
+struct WorkItem {     // one strip (<= 256 rows) of image 1 against all of image 2
   uint32_t a_row;     // pool row of the strip
   uint32_t b_row;     // pool row of image 2
   uint32_t n_btiles;  // number of 256-column tiles
   uint32_t pair;      // index into PairMeta (batch-local)
-  uint32_t m_tiles;   // 1 or 2 row blocks of 256 rows (128 per CTA of the pair) in this strip
+  uint32_t m_tiles;   // 1 or 2 accumulator row blocks (128 rows each) in this strip
 };
 
 struct TopTwo {
@@ -79,62 +79,62 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 }
 
 // =====================================================================================
-// Production score kernel, one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 512-row strip:
-// TMA -> swizzled smem -> tcgen05.mma.cta_group::2 kind::i8 (M = 256 over the pair) -> TMEM -> filter -> rescore
+// Production score kernel: TMA -> swizzled smem -> tcgen05.mma kind::i8 -> TMEM -> filter -> insert
 //
-// Why a pair: with one CTA the MMA reads A (4 KB) + B (8 KB) from shared memory every 128 cycles while
-// TMA writes the next B tile, which saturates the 128 B/clk shared-memory port (measured: the tensor
-// pipe stalls at ~60 %).  In a pair each CTA feeds its own 128 rows of A and only HALF of B (4 KB),
-// and loads only half of every B tile from L2.
+//   warp 0        TMA producer: A strip (2 x 128 rows, kept for the whole item) + ring of B tiles (256 rows)
+//   warp 1        MMA issuer: per B tile two accumulator tiles (strip rows 0-127 / 128-255), 4 x K32 each,
+//                 ping-pong between the two 256-column halves of TMEM
+//   warps 4-11    filter epilogue: tcgen05.ld + 3-input max tree over each thread's four 32-column runs;
+//                 the accumulator buffer is released as soon as it has been read.  A run whose maximum
+//                 reaches min_score is copied, exact scores and all, from registers to a shared-memory
+//                 mailbox (a few vector stores; rare).
+//   warps 2,3     insert: lane l examines column l of every posted run and feeds scores >= min_score to
+//                 the top-2 accumulators (global atomics whose latency is off the tile pipeline).
 //
-//   warp 0        TMA producer (both CTAs): own A rows (2 x 128, kept for the whole item) + ring of B
-//                 half tiles (128 descriptors); byte counts are reported to the leader CTA's barriers
-//   warp 1        MMA issuer (leader CTA only): per B tile two accumulator tiles (row blocks 0 / 1),
-//                 4 x K32 each, ping-pong between the two 256-column halves of TMEM; completion is
-//                 multicast to both CTAs' barriers
-//   warps 4-11    filter epilogue (both CTAs, own 128 accumulator rows): tcgen05.ld + 3-input max tree
-//                 over each thread's 32-column run; the accumulator buffer is released (to the leader)
-//                 as soon as it has been read.  A run whose maximum reaches min_score is not re-read:
-//                 its (row, 32-column run) address goes to a shared-memory staging ring.
-//   warps 2,3     insert: feed survivors to the top-2 accumulators (global atomics, off the tile pipeline);
-//                 runs with several survivors are first re-scored exactly on CUDA cores (__dp4a).
+// (A cta_group::2 variant -- CTA pairs sharing each B tile -- was built and measured slower on this
+// workload: with K = 128 the tile pipeline is bound by the accumulator hand-off latency, which the
+// cross-CTA barriers lengthen; see DESIGN.md "Kernel history".)
 // =====================================================================================
-constexpr int kStages = 6;                     // ring of B half tiles (128 descriptors each)
-constexpr int kAStages = 2;                    // A ring (next item's rows prefetched)
-constexpr int kMTile = 128;                    // accumulator rows per CTA (UMMA M = 256 over the pair)
-constexpr int kABytes = 2 * kMTile * kDim;     // 32 KiB per CTA: its 128 rows of both row blocks
-constexpr int kBBytes = (kTileCols / 2) * kDim;  // 16 KiB per CTA: its half of a 256-column B tile
-constexpr int kEpiWarps = 16;                  // 4 per TMEM lane quarter, 64 accumulator columns each
-constexpr int kEpiCols = kTileCols / (kEpiWarps / 4);
-constexpr int kRescoreWarps = 2;               // insert / re-score warps
-constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4-19 epilogue
+constexpr int kStages = 4;                     // B-tile ring
+constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
+constexpr int kMTile = 128;                    // UMMA M
+constexpr int kABytes = 2 * kMTile * kDim;     // 32 KiB (two 128-row boxes)
+constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
+constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter (one per 128-column half)
+constexpr int kEpiCols = kTileCols / 2;        // 128 accumulator columns per warp and tile
+constexpr int kInsertWarps = 2;                // warps 2 and 3
+constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4-11 epilogue
 constexpr int kScoreThreads = 32 * kScoreWarps;
-constexpr int kRunCols = 32;                   // columns per thread per tcgen05.ld == rescoring granularity
-constexpr int kRunsPerWarp = kEpiCols / kRunCols;
-constexpr int kMailSlots = 32;                 // per epilogue warp: ring of pending records (>= 32: one post can carry 32)
-constexpr int kStageSlots = 1;                 // per rescoring warp: descriptor staging buffer
-constexpr int kHitBytes = kDim + kRunCols * kDim;  // one image-1 descriptor + 32 image-2 descriptors
-constexpr uint32_t kDirectTag = 0xFFFFFFFFu;
-static_assert(kRunsPerWarp == 2, "epilogue code is written for two 32-column runs per warp");
+constexpr int kRunCols = 32;                   // accumulator columns per thread per tcgen05.ld
+constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 4, all in flight at once
+constexpr int kMailSlots = 16;                 // per epilogue warp: ring of survivor runs
+constexpr int kPostChunk = 8;                  // lanes of one warp that may post in one go (<= kMailSlots / 2)
+constexpr int kInsertBatch = 4;                // runs an insert warp handles per L2 round trip
+static_assert(kRunsPerWarp == 4, "epilogue code is written for four 32-column runs per warp");
+
+// A 32-column run of one accumulator row that holds at least one score >= min_score, copied out of the
+// epilogue thread's registers: the exact scores themselves, no recomputation.
+struct HitRun {
+  uint32_t row_slot;   // accumulator slot of the row
+  uint32_t col_slot0;  // accumulator slot of the run's first column
+  uint32_t pad_[2];
+  uint32_t v[kRunCols];
+};
+static_assert(sizeof(HitRun) == 144, "HitRun layout");
 
 struct ScoreShared {
   uint64_t a_full[kAStages], a_empty[kAStages];
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t t_full[2], t_empty[2];
-  uint64_t h_full[kRescoreWarps][kStageSlots];  // staging: the hit's descriptors have landed (tx-count barrier)
-  uint32_t mail_head[kEpiWarps];   // records written by epilogue warp e (monotonic)
-  uint32_t mail_tail[kEpiWarps];   // records consumed by its rescoring warp (monotonic)
-  uint32_t epi_done;               // epilogue warps that have finished
+  uint32_t mail_head[kEpiWarps];  // runs posted by epilogue warp e (monotonic)
+  uint32_t mail_tail[kEpiWarps];  // runs consumed by its insert warp (monotonic)
+  uint32_t epi_done;              // epilogue warps that have finished
   uint32_t tmem_base;
-  // Records.  Survivor (the common case, exact score already known from the accumulator):
-  //   {row accumulator slot, column accumulator slot, score, kDirectTag}
-  // Run with several survivors (rare; re-scored on CUDA cores):
-  //   {pool row of the image-1 descriptor, pool row of the run's first image-2 descriptor,
-  //    row accumulator slot, accumulator slot of the run's first column}
-  uint4 mail[kEpiWarps][kMailSlots];
+  uint32_t pad_[2];
+  uint4 jobs[kInsertWarps][32];   // per insert warp: compacted (row slot, column slot, score) insertions
+  HitRun mail[kEpiWarps][kMailSlots];
 };
-constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes +
-                                kRescoreWarps * kStageSlots * kHitBytes + (int)sizeof(ScoreShared);
+constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + (int)sizeof(ScoreShared);
 static_assert(kScoreSmemBytes <= 227 * 1024, "shared memory budget");
 
 // max over 32 accumulator entries with 3-input integer max (VIMNMX3), as a tree for ILP:
@@ -157,153 +157,161 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
   return v;
 }
-
-// Epilogue side (warp-uniform call): lanes with `hit` append one record each to this warp's mailbox.
-// Single producer (this warp) / single consumer (its rescoring warp): no atomics, a few instructions.
-__device__ __forceinline__ void mail_post(ScoreShared* sh, uint32_t e, uint32_t lane, bool hit, uint4 rec, uint32_t& head) {
-  const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-  if (ballot == 0) return;
-  if (hit) {
-    const uint32_t pos = head + __popc(ballot & ((1u << lane) - 1));
-    uint32_t spins = 0;
-    while (pos - ld_volatile_shared(&sh->mail_tail[e]) >= (uint32_t)kMailSlots) {  // ring full: back-pressure
-      if (++spins > (1u << 28)) __trap();
-    }
-    sh->mail[e][pos % kMailSlots] = rec;
-  }
-  head += __popc(ballot);
-  fence_cta();
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = head;
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Survivors of one 32-column run held in registers: bit e of the result is set iff v[e] >= min_score.
-__device__ __forceinline__ uint32_t survivor_mask(const uint32_t (&v)[32], int min_score) {
-  uint32_t mask = 0;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) mask |= ((int)v[e] >= min_score) ? (1u << e) : 0u;
-  return mask;
-}
-
-// Insert warp r serves the mailboxes of epilogue warps r, r + 2, r + 4, ...  Each lane takes one record.
-// Survivor records go straight to the top-2 accumulators (32 insertions in flight per warp).  A record
-// naming a run with several survivors is re-scored by the whole warp: the bulk-copy engine stages the
-// 1 + 32 descriptors (L2 -> shared memory), lane l recomputes the exact score of column (run + l) with
-// __dp4a (bank-conflict-free rotation) and inserts it if it reaches min_score.
-__device__ __forceinline__ void insert_loop(ScoreShared* sh, uint32_t smem_stage, const uint8_t* __restrict__ pool,
-                                            TopTwo* __restrict__ acc, int min_score, uint32_t r, uint32_t lane,
-                                            unsigned long long* cand_counter, uint32_t dbg) {
-  uint32_t tail[kEpiWarps / kRescoreWarps];
-#pragma unroll
-  for (int k = 0; k < kEpiWarps / kRescoreWarps; ++k) tail[k] = 0;
-  uint32_t count = 0, staged = 0;
-  const uint32_t bar = ptx::smem_u32(&sh->h_full[r][0]);
-  const uint32_t base = smem_stage + r * kStageSlots * kHitBytes;
-  for (;;) {
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < kEpiWarps / kRescoreWarps; ++k) {
-      const uint32_t e = r + k * kRescoreWarps;
-      const uint32_t head = ld_volatile_shared(&sh->mail_head[e]);
-      const uint32_t avail = head - tail[k];
-      if (avail == 0) continue;
-      any = true;
-      fence_cta();
-      const uint32_t n = avail < 32u ? avail : 32u;
-      uint4 rec = make_uint4(0, 0, 0, 0);
-      if (lane < n)
-        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w)
-                     : "r"(ptx::smem_u32(&sh->mail[e][(tail[k] + lane) % kMailSlots]))
-                     : "memory");
-      tail[k] += n;
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_tail[e]) = tail[k];  // entries may be reused
-      const bool direct = lane < n && rec.w == kDirectTag;
-      if (direct && !(dbg & 8)) {
-        top2_insert2(acc, rec.x, rec.y, rec.z);
-        ++count;
+// Epilogue side (warp-uniform call).  Lanes whose run maximum reaches min_score copy the run (32 exact
+// scores, still in registers) into this warp's mailbox.  Single producer (this warp) / single consumer
+// (its insert warp): no atomics.  At most kPostChunk lanes post per round so a small ring cannot deadlock.
+__device__ __forceinline__ void post_run(ScoreShared* sh, uint32_t e, uint32_t lane, const uint32_t (&v)[32], bool hit,
+                                         uint32_t row_slot, uint32_t col_slot0, uint32_t& head) {
+  uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+  while (ballot) {
+    const uint32_t rank = __popc(ballot & ((1u << lane) - 1));
+    const bool mine = hit && rank < (uint32_t)kPostChunk;
+    if (mine) {
+      const uint32_t pos = head + rank;
+      uint32_t spins = 0;
+      while (pos - ld_volatile_shared(&sh->mail_tail[e]) >= (uint32_t)kMailSlots) {  // ring full: back-pressure
+        if (++spins > (1u << 28)) __trap();
       }
-      uint32_t multi = __ballot_sync(0xffffffffu, lane < n && rec.w != kDirectTag);
-      while (multi) {  // rare: warp-cooperative re-scoring, one run at a time
-        const int src = __ffs(multi) - 1;
-        multi &= multi - 1;
-        const uint32_t a_row = __shfl_sync(0xffffffffu, rec.x, src), b_row = __shfl_sync(0xffffffffu, rec.y, src);
-        const uint32_t row_slot = __shfl_sync(0xffffffffu, rec.z, src), col_slot0 = __shfl_sync(0xffffffffu, rec.w, src);
-        if (lane == 0) {
-          ptx::mbar_arrive_expect_tx(bar, kHitBytes);
-          ptx::bulk_load(base, pool + (size_t)a_row * kDim, kDim, bar);
-          ptx::bulk_load(base + kDim, pool + (size_t)b_row * kDim, kRunCols * kDim, bar);
-        }
-        ptx::mbar_wait(bar, staged & 1);
-        ++staged;
-        uint32_t sc = 0;
+      const uint32_t dst = ptx::smem_u32(&sh->mail[e][pos % kMailSlots]);
+      st_shared_v4(dst, row_slot, col_slot0, 0u, 0u);
 #pragma unroll
-        for (int q = 0; q < kDim / 4; ++q) {
-          const uint32_t w = (lane + q) & 31;  // rotation: every lane touches a different bank in each step
-          uint32_t av, bv;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(av) : "r"(base + w * 4));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bv) : "r"(base + kDim + lane * kDim + w * 4));
-          sc = __dp4a(av, bv, sc);
+      for (int q = 0; q < kRunCols / 4; ++q)
+        st_shared_v4(dst + 16 + q * 16, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      hit = false;
+    }
+    const uint32_t posted = __ballot_sync(0xffffffffu, mine);
+    head += __popc(posted);
+    ballot &= ~posted;
+    fence_cta();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = head;
+  }
+}
+
+// Insert warp r serves the mailboxes of epilogue warps r, r + 2, r + 4, r + 6.  Lane l looks at column
+// (run + l) of every run: a score >= min_score is a survivor and goes to the top-2 accumulators of its row
+// and its column.  Up to kInsertBatch runs are taken per pass and their survivors are compacted onto
+// consecutive lanes, so all insertions of a pass share one L2 round trip.
+__device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict__ acc, int min_score,
+                                            uint32_t r, uint32_t lane, unsigned long long* cand_counter, uint32_t dbg) {
+  constexpr int kBoxes = kEpiWarps / kInsertWarps;
+  uint32_t tail[kBoxes];
+#pragma unroll
+  for (int k = 0; k < kBoxes; ++k) tail[k] = 0;
+  uint32_t count = 0;
+  for (;;) {
+    uint32_t row_slot[kInsertBatch], col_slot[kInsertBatch], sc[kInsertBatch];
+    uint32_t got = 0;
+#pragma unroll
+    for (int b = 0; b < kInsertBatch; ++b) {
+      row_slot[b] = col_slot[b] = 0;
+      sc[b] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kBoxes; ++k) {
+      const uint32_t e = r + k * kInsertWarps;
+      const uint32_t head = ld_volatile_shared(&sh->mail_head[e]);
+      uint32_t took = 0;
+#pragma unroll
+      for (int b = 0; b < kInsertBatch; ++b) {
+        if (got == (uint32_t)b && tail[k] != head) {  // warp-uniform
+          if (took == 0) fence_cta();
+          const uint32_t src = ptx::smem_u32(&sh->mail[e][tail[k] % kMailSlots]);
+          uint32_t rs, cs;
+          asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rs), "=r"(cs) : "r"(src) : "memory");
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(sc[b]) : "r"(src + 16 + lane * 4) : "memory");
+          row_slot[b] = rs;
+          col_slot[b] = cs + lane;
+          ++tail[k];
+          ++took;
+          ++got;
         }
-        __syncwarp();  // every lane has read the staging buffer before it is refilled
-        if ((int)sc >= min_score) {  // pool padding rows are zero and can never get here
-          top2_insert2(acc, row_slot, col_slot0 + lane, sc);
+      }
+      if (took) {
+        __syncwarp();  // every lane has read the entries before they may be reused
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_tail[e]) = tail[k];
+      }
+    }
+    if (got) {
+      // compact the survivors of the batch: survivor (run b, lane) becomes job pre[b] + (its rank in run b);
+      // lane j then performs job j, so every insertion of the batch is in flight in the same instructions
+      uint32_t bal[kInsertBatch], pre[kInsertBatch + 1];
+      pre[0] = 0;
+#pragma unroll
+      for (int b = 0; b < kInsertBatch; ++b) {
+        bal[b] = __ballot_sync(0xffffffffu, (int)sc[b] >= min_score);
+        pre[b + 1] = pre[b] + __popc(bal[b]);
+      }
+      const uint32_t total = (dbg & 8) ? 0u : pre[kInsertBatch];
+      for (uint32_t base = 0; base < total; base += 32) {
+#pragma unroll
+        for (int b = 0; b < kInsertBatch; ++b) {
+          const uint32_t job = pre[b] + __popc(bal[b] & ((1u << lane) - 1));
+          if ((int)sc[b] >= min_score && job - base < 32u)
+            st_shared_v4(ptx::smem_u32(&sh->jobs[r][job - base]), row_slot[b], col_slot[b], sc[b], 0u);
+        }
+        __syncwarp();
+        if (base + lane < total) {
+          uint32_t jr, jc, js, jp;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(jr), "=r"(jc), "=r"(js), "=r"(jp)
+                       : "r"(ptx::smem_u32(&sh->jobs[r][lane]))
+                       : "memory");
+          top2_insert2(acc, jr, jc, js);
           ++count;
         }
+        __syncwarp();
       }
-    }
-    if (!any) {
+    } else {
       if (ld_volatile_shared(&sh->epi_done) == (uint32_t)kEpiWarps) {
         fence_cta();
         bool drained = true;
 #pragma unroll
-        for (int k = 0; k < kEpiWarps / kRescoreWarps; ++k)
-          if (ld_volatile_shared(&sh->mail_head[r + k * kRescoreWarps]) != tail[k]) drained = false;
+        for (int k = 0; k < kBoxes; ++k)
+          if (ld_volatile_shared(&sh->mail_head[r + k * kInsertWarps]) != tail[k]) drained = false;
         if (drained) break;  // epi_done is bumped only after that warp's last post is visible
       } else {
-        __nanosleep(256);
+        __nanosleep(200);
       }
     }
   }
   if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kScoreThreads, 1)
-score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ pool,
-                     const WorkItem* __restrict__ items, uint32_t n_items, const PairMeta* __restrict__ pairs,
-                     TopTwo* __restrict__ acc, int min_score, unsigned long long* cand_counter, uint32_t dbg) {
-  // dbg (bring-up timing experiments only, results become meaningless): 1 = epilogue releases tiles unread,
-  // 2 = B tiles are not loaded, 4 = hits are not posted, 8 = hits are not rescored, 16 = hits are not staged
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
+                     const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
+                     unsigned long long* cand_counter, uint32_t dbg) {
+  // dbg (bring-up timing experiments only, results become meaningless):
+  // 2 = B tiles are not loaded, 4 = survivor runs are not posted, 8 = survivors are not inserted
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem0;
   const uint32_t smem_b = smem0 + kAStages * kABytes;
-  const uint32_t smem_stage = smem_b + kStages * kBBytes;
-  ScoreShared* sh = reinterpret_cast<ScoreShared*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes +
-                                                   kStages * kBBytes + kRescoreWarps * kStageSlots * kHitBytes);
+  ScoreShared* sh =
+      reinterpret_cast<ScoreShared*>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + kAStages * kABytes + kStages * kBBytes);
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
-  const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap);
     for (int s = 0; s < kAStages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&sh->a_full[s]), 1);   // leader's producer arrives; both CTAs' bytes count
-      ptx::mbar_init(ptx::smem_u32(&sh->a_empty[s]), 1);  // multicast commit
+      ptx::mbar_init(ptx::smem_u32(&sh->a_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->a_empty[s]), 1);
     }
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&sh->b_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&sh->b_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&sh->t_full[s]), 1);               // multicast commit
-      ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), 2 * kEpiWarps);  // epilogue warps of BOTH CTAs (leader's copy is used)
+      ptx::mbar_init(ptx::smem_u32(&sh->t_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), kEpiWarps);
     }
-    for (int r = 0; r < kRescoreWarps; ++r)
-      for (int s = 0; s < kStageSlots; ++s) ptx::mbar_init(ptx::smem_u32(&sh->h_full[r][s]), 1);
     for (int e = 0; e < kEpiWarps; ++e) {
       sh->mail_head[e] = 0;
       sh->mail_tail[e] = 0;
@@ -311,49 +319,48 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
     sh->epi_done = 0;
     ptx::fence_barrier_init();
   }
-  ptx::cluster_sync();  // both CTAs resident and their barriers initialised before anything crosses the pair
-  if (warp == 2) {      // one warp per CTA: paired TMEM allocation (all 512 columns: two 256-column accumulators)
-    ptx::tmem_alloc_512_2sm(ptx::smem_u32(&sh->tmem_base));
-    ptx::tmem_relinquish_2sm();
+  if (warp == 2) {  // whole warp: TMEM allocation (all 512 columns: two 256-column accumulators)
+    ptx::tmem_alloc_512(ptx::smem_u32(&sh->tmem_base));
+    ptx::tmem_relinquish();
   }
   ptx::tcgen05_fence_before();
-  ptx::cluster_sync();
+  __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one lane, both CTAs)
+    // ------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      for (uint32_t it = pair_id; it < n_items; it += n_pairs) {
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
         ptx::mbar_wait(ptx::smem_u32(&sh->a_empty[as]), aph ^ 1);
         const uint32_t afull = ptx::smem_u32(&sh->a_full[as]);
-        if (rank == 0) ptx::mbar_arrive_expect_tx(afull, 2 * w.m_tiles * (kABytes / 2));  // both CTAs' bytes
+        ptx::mbar_arrive_expect_tx(afull, w.m_tiles * (kABytes / 2));
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh)
-          ptx::tma_load_2d_2sm(smem_a + as * kABytes + mh * (kABytes / 2), &tmap, afull, 0,
-                               (int32_t)(w.a_row + mh * 2 * kMTile + rank * kMTile));
+          ptx::tma_load_2d(smem_a + as * kABytes + mh * (kABytes / 2), &tmap, afull, 0, (int32_t)(w.a_row + mh * kMTile));
         if (++as == kAStages) { as = 0; aph ^= 1; }
         for (uint32_t t = 0; t < w.n_btiles; ++t) {
           ptx::mbar_wait(ptx::smem_u32(&sh->b_empty[bs]), bph ^ 1);
           const uint32_t full = ptx::smem_u32(&sh->b_full[bs]);
           if (dbg & 2) {
-            if (rank == 0) ptx::mbar_arrive(full);
+            ptx::mbar_arrive(full);
           } else {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(full, 2 * kBBytes);
-            ptx::tma_load_2d_2sm(smem_b + bs * kBBytes, &tmap, full, 0,
-                                 (int32_t)(w.b_row + t * kTileCols + rank * (kTileCols / 2)));
+            ptx::mbar_arrive_expect_tx(full, kBBytes);
+            const int32_t r = (int32_t)(w.b_row + t * kTileCols);
+            ptx::tma_load_2d(smem_b + bs * kBBytes, &tmap, full, 0, r);
+            ptx::tma_load_2d(smem_b + bs * kBBytes + kBBytes / 2, &tmap, full, 0, r + kTileCols / 2);
           }
           if (++bs == kStages) { bs = 0; bph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(2 * kMTile, kTileCols);
+    // ------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kMTile, kTileCols);
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
-      for (uint32_t it = pair_id; it < n_items; it += n_pairs) {
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const uint32_t n_btiles = items[it].n_btiles, m_tiles = items[it].m_tiles;
         ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
         const uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
@@ -367,73 +374,55 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
             const uint32_t d = tmem_base + ts * kTileCols;
 #pragma unroll
             for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
-              ptx::umma_i8_2sm(d, adesc + k * 2, bdesc + k * 2, idesc, k);
-            ptx::umma_commit_2sm(ptx::smem_u32(&sh->t_full[ts]), 3);
+              ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+            ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
             if (++ts == 2) { ts = 0; tph ^= 1; }
           }
-          ptx::umma_commit_2sm(ptx::smem_u32(&sh->b_empty[bs]), 3);
+          ptx::umma_commit(ptx::smem_u32(&sh->b_empty[bs]));
           if (++bs == kStages) { bs = 0; bph ^= 1; }
         }
-        ptx::umma_commit_2sm(ptx::smem_u32(&sh->a_empty[as]), 3);
+        ptx::umma_commit(ptx::smem_u32(&sh->a_empty[as]));
         if (++as == kAStages) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-    // ------------------------------------------------------------ filter epilogue (16 warps, both CTAs)
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ filter epilogue (8 warps)
     const uint32_t e = warp - 4;
-    const uint32_t quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are visible to this warp
-    const uint32_t col0 = (e >> 2) * kEpiCols;    // this warp's 64 of the tile's 256 columns
+    const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are visible to this warp
+    const uint32_t col0 = (e >> 2) * kEpiCols;  // which 128 of the tile's 256 columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
     uint32_t ts = 0, tph = 0, mail_head = 0;
-    for (uint32_t it = pair_id; it < n_items; it += n_pairs) {
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairMeta pm = pairs[w.pair];
-      const uint32_t a_row = w.a_row + rank * kMTile + quarter * 32 + lane;  // pool row of this thread's descriptor (mh = 0)
-      const uint32_t row_slot = pm.acc_off + (a_row - pm.a_row0);            // its accumulator slot
+      // accumulator slot of this thread's row (mh = 0) and of this warp's first column
+      const uint32_t row_slot = pm.acc_off + (w.a_row - pm.a_row0) + quarter * 32 + lane;
       const uint32_t col_slot0 = pm.acc_off + pm.n1 + col0;
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + col0;
-          int mc0 = 0, mc1 = 0;
-          uint32_t v0[32], v1[32];  // both runs in flight; ptxas tracks each load's registers
-          if (dbg & 1) {
-#pragma unroll
-            for (int x = 0; x < 32; ++x) v0[x] = v1[x] = 0;
-          } else {
-            ptx::tmem_ld_32x32b_x32(taddr, v0);
-            ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
-            ptx::tmem_wait_ld();
-            mc0 = max_tree32(v0);
-            mc1 = max_tree32(v1);
-          }
-          // the accumulator values are in registers: hand the TMEM buffer back to the leader's MMA warp
+          uint32_t v0[32], v1[32], v2[32], v3[32];  // all four runs in flight; ptxas tracks each load's registers
+          ptx::tmem_ld_32x32b_x32(taddr, v0);
+          ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
+          ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
+          ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
+          ptx::tmem_wait_ld();
+          const int mc0 = max_tree32(v0), mc1 = max_tree32(v1), mc2 = max_tree32(v2), mc3 = max_tree32(v3);
+          // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp
           ptx::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            const uint32_t bar = ptx::smem_u32(&sh->t_empty[ts]);
-            if (rank == 0) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(bar, 0);
-          }
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
-          if (__any_sync(0xffffffffu, max(mc0, mc1) >= min_score) && !(dbg & 4)) {
-            // rare: some run holds a survivor.  The exact score is the run maximum already in registers;
-            // only a run with SEVERAL survivors has to be re-scored by the insert warps.
-            const uint32_t arow = a_row + mh * 2 * kMTile, rslot = row_slot + mh * 2 * kMTile;
-            const uint32_t brow = w.b_row + t * kTileCols + col0, cslot = col_slot0 + t * kTileCols;
-            if (__any_sync(0xffffffffu, mc0 >= min_score)) {
-              const uint32_t mask = survivor_mask(v0, min_score);
-              const uint4 rec = __popc(mask) == 1 ? make_uint4(rslot, cslot + __ffs(mask) - 1, (uint32_t)mc0, kDirectTag)
-                                                  : make_uint4(arow, brow, rslot, cslot);
-              mail_post(sh, e, lane, mask != 0, rec, mail_head);
-            }
-            if (__any_sync(0xffffffffu, mc1 >= min_score)) {
-              const uint32_t mask = survivor_mask(v1, min_score);
-              const uint4 rec = __popc(mask) == 1
-                                    ? make_uint4(rslot, cslot + kRunCols + __ffs(mask) - 1, (uint32_t)mc1, kDirectTag)
-                                    : make_uint4(arow, brow + kRunCols, rslot, cslot + kRunCols);
-              mail_post(sh, e, lane, mask != 0, rec, mail_head);
-            }
+          if (__any_sync(0xffffffffu, max(max(mc0, mc1), max(mc2, mc3)) >= min_score) && !(dbg & 4)) {
+            // rare: some run holds a survivor; the lanes concerned hand the run to the insert warps.
+            // Pool padding rows are all-zero descriptors (score 0 < min_score), so no bounds test is needed.
+            const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
+            post_run(sh, e, lane, v0, mc0 >= min_score, rslot, cslot, mail_head);
+            post_run(sh, e, lane, v1, mc1 >= min_score, rslot, cslot + kRunCols, mail_head);
+            post_run(sh, e, lane, v2, mc2 >= min_score, rslot, cslot + 2 * kRunCols, mail_head);
+            post_run(sh, e, lane, v3, mc3 >= min_score, rslot, cslot + 3 * kRunCols, mail_head);
           }
         }
       }
@@ -444,20 +433,18 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
       atomicAdd(&sh->epi_done, 1u);
     }
   } else {
-    // ------------------------------------------------------------ insert / re-score (warps 2, 3)
-    insert_loop(sh, smem_stage, pool, acc, min_score, warp - 2, lane, cand_counter, dbg);
+    // ------------------------------------------------------------ insert (warps 2, 3)
+    insert_loop(sh, acc, min_score, warp - 2, lane, cand_counter, dbg);
   }
 
-  // the peer's shared memory and TMEM are read by MMAs the leader issued: leave together
   ptx::tcgen05_fence_before();
-  ptx::cluster_sync();
+  __syncthreads();
   if (warp == 2) {
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc_512_2sm(tmem_base);
+    ptx::tmem_dealloc_512(tmem_base);
   }
 }
 
-// =====================================================================================
 // Test-only device cross-check: the same contract on CUDA cores (__dp4a), no tensor cores,
 // no TMA.  Selected with SMB_ENGINE_DP4A; never the default.
 // =====================================================================================
@@ -476,7 +463,7 @@ score_dp4a_kernel(const uint8_t* __restrict__ pool, const WorkItem* __restrict__
   for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const WorkItem w = items[it];
     const PairMeta pm = pairs[w.pair];
-    for (uint32_t mh = 0; mh < 2 * w.m_tiles; ++mh) {  // 128-row sub-blocks of the strip
+    for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
       const uint32_t a_row = w.a_row + mh * kMTile;
       const uint32_t* ga = reinterpret_cast<const uint32_t*>(pool + (size_t)a_row * kDim);
       __syncthreads();

@@ -612,7 +612,7 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
       for (uint32_t r = 0; r < m.n1; r += kStripRows)
         h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first),
-                                      m.n1 - r > 2u * (uint32_t)kMTile ? 2u : 1u};
+                                      m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
     }
     std::stable_sort(h->h_items.p, h->h_items.p + ni,
                      [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
@@ -627,9 +627,8 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
       if (h->opts.engine == SMB_ENGINE_TCGEN05) {
         if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
-        // one CTA pair (cluster of 2) per work item, persistent over the item list
-        const unsigned grid = 2u * (unsigned)std::min<size_t>(ni, (size_t)h->num_sms / 2);
-        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
+        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);  // persistent CTAs
+        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
                                                                           h->d_acc.p, h->filter.min_score, cand, h->dbg_flags);
       } else {
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
