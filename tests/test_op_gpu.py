@@ -1,0 +1,80 @@
+"""The Scanner op end to end on the GPU, driven the way integration/feature_matching.py drives it
+(stencil range(0, overlap), packets of packet_size rows, REPEAT_EDGE at the table tail), against the oracle's
+restatement of the reference op's pair loop (sequential_matching.cc:139-181)."""
+import numpy as np
+import pytest
+
+from scanner_colmap_b200 import scanner_sim, synth, wire
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    from oracle import oracle as o
+    return o
+
+
+def _expected_rows(oracle, ids, descs, overlap, min_num_inliers=15, **opts):
+    rows = []
+    for r in range(len(ids)):
+        partners = oracle.row_partners(ids, r, overlap)
+        tv = []
+        for pid in partners:
+            m = oracle.match(descs[r], descs[ids.index(pid)], **opts)
+            tv.append(m if len(m) >= min_num_inliers else np.empty((0, 2), np.uint32))   # sequential_matching.cc:173-178
+        rows.append((partners, tv))
+    return rows
+
+
+@pytest.mark.parametrize("packet_size", [4, 25])
+def test_feature_matching_config1_shape(oracle, packet_size):
+    """BASELINE.json configs[0] (sequential overlap=10, packet_size=4 on 20 images), at 1024 descriptors per image
+    so the CPU oracle finishes in seconds; test_gpu_parity covers 20 x 4096 through the C ABI."""
+    n = 20
+    ids = [1000 + 3 * k for k in range(n)]                     # ids need not be 0..n-1
+    sizes = [1024 if k % 5 else 700 + k for k in range(n)]
+    descs = [synth.make_image(i, s, track_step=48) for i, s in zip(ids, sizes)]
+    kps = [np.zeros((s, 6), np.float32) for s in sizes]
+    got_ids, got_tvg = scanner_sim.run_feature_matching(ids, kps, descs, overlap=10, packet_size=packet_size)
+    want = _expected_rows(oracle, ids, descs, 10)
+    assert len(got_ids) == len(got_tvg) == n
+    total_pairs = 0
+    for r, (partners, tv) in enumerate(want):
+        assert got_ids[r] == partners, f"row {r}"
+        assert len(got_tvg[r]) == len(partners)
+        for g, w in zip(got_tvg[r], tv):
+            assert np.array_equal(g.inlier_matches, w)
+            assert g.config == 0 and not g.E.any() and not g.F.any() and not g.H.any()
+        total_pairs += len(partners)
+    assert total_pairs == 135 and got_ids[-1] == []            # last row: only repeated edge rows, n = 0
+    assert sum(len(g.inlier_matches) for row in got_tvg for g in row) > 1000
+
+
+def test_kernel_args_reach_the_matcher(oracle):
+    ids = [1, 2, 3]
+    descs = [synth.make_image(i, 400, track_step=16, noise=0.2) for i in ids]
+    kps = [np.zeros((400, 6), np.float32)] * 3
+    args = wire.encode_matching_args(max_ratio=0.95, max_distance=1.0, cross_check=False, min_num_inliers=1)
+    got_ids, got_tvg = scanner_sim.run_feature_matching(ids, kps, descs, overlap=3, packet_size=2, args=args)
+    want = _expected_rows(oracle, ids, descs, 3, min_num_inliers=1, max_ratio=0.95, max_distance=1.0, cross_check=False)
+    for r, (partners, tv) in enumerate(want):
+        assert got_ids[r] == partners
+        for g, w in zip(got_tvg[r], tv):
+            assert np.array_equal(g.inlier_matches, w)
+
+
+def test_duplicate_ids_and_empty_images(oracle):
+    """An id repeated inside the stencil is matched once; images without descriptors yield empty geometries."""
+    ids = [5, 6, 6, 7, 8]
+    sizes = [300, 200, 200, 0, 260]
+    base = {i: synth.make_image(i, s, track_step=16) for i, s in zip(ids, sizes)}
+    descs = [base[i] for i in ids]
+    kps = [np.zeros((len(d), 6), np.float32) for d in descs]
+    got_ids, got_tvg = scanner_sim.run_feature_matching(ids, kps, descs, overlap=4, packet_size=3)
+    assert got_ids[0] == [6, 7] and got_ids[1] == [7, 8] and got_ids[2] == [7, 8] and got_ids[4] == []
+    for r in range(len(ids)):
+        for pid, g in zip(got_ids[r], got_tvg[r]):
+            w = oracle.match(descs[r], base[pid])
+            w = w if len(w) >= 15 else np.empty((0, 2), np.uint32)
+            assert np.array_equal(g.inlier_matches, w)
