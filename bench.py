@@ -30,6 +30,8 @@ IMAGES_PER_GPU = 100
 N_DESC = 8192
 OVERLAP = 10
 INT8_SPEC_TOPS = 4500.0  # B200 dense INT8, NVIDIA datasheet
+WORKLOAD = (f"{IMAGES_PER_GPU} images x {N_DESC} descriptors per GPU, sequential overlap={OVERLAP}, cross_check on "
+            "(BASELINE.json configs[1])")
 
 
 def _env_int(name, default):
@@ -143,8 +145,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{IMAGES_PER_GPU} images x {N_DESC} descriptors, sequential overlap={OVERLAP}, "
-                               f"cross_check on (BASELINE.json configs[1]); each step = {sample} of its pairs",
+        "config": {"workload": WORKLOAD, "sample": f"each step = {sample} of the workload's 855 pairs (bounded CPU sample)",
                    "note": "CPU restatement of COLMAP MatchSiftFeaturesCPU (oracle/sift_match_oracle.c, gcc -O3 "
                            "-march=x86-64-v3, OpenMP over pairs); the Eigen/COLMAP/Scanner binary is unbuildable here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
@@ -203,39 +204,33 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- workload: this rank's 100 images (+ 9 halo images owned by the next rank)
-    first = rank * IMAGES_PER_GPU
-    own_ids = list(range(first, first + IMAGES_PER_GPU))
-    halo_ids = list(range(first + IMAGES_PER_GPU, first + IMAGES_PER_GPU + OVERLAP - 1)) if rank + 1 < world else []
+    # ---- workload: 100 * world images in one sequence; this rank's contiguous anchor window + its halo
+    from scanner_colmap_b200 import sharding
+    sizes = [N_DESC] * (IMAGES_PER_GPU * world)
+    sp = sharding.plan(sizes, OVERLAP, world, rank)
+    own_ids = list(range(*sp.own))
+    halo_ids = [row for row, _ in sp.recv]
     imgs = [torch.from_numpy(synth.make_image(i, N_DESC)).pin_memory() for i in own_ids]
     imgs_np = [t.numpy() for t in imgs]
-    all_ids = own_ids + halo_ids
-    pairs = sequential_pairs(all_ids, OVERLAP)
-    pairs = pairs[pairs[:, 0] < first + IMAGES_PER_GPU]  # anchors this rank owns
+    pairs = sp.pairs                      # table row == image id here
     h2d = sum(a.nbytes for a in imgs_np)
 
     m = SiftMatcher(device=local, profile=True)
     stream = torch.cuda.ExternalStream(m.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    halo_buf = torch.empty((len(halo_ids) * N_DESC, 128), dtype=torch.uint8, device=dev) if halo_ids else None
+    halo_buf = {row: torch.empty(N_DESC * 128, dtype=torch.uint8, device=dev) for row in halo_ids}
 
     def halo_exchange():
-        """Rank r receives the first overlap-1 images of rank r+1 straight from its descriptor pool."""
+        """Halo rows come straight out of the owning rank's descriptor pool (zero-copy view) over NCCL."""
         if world == 1:
             return
-        reqs = []
-        if rank > 0:
-            for i in own_ids[:OVERLAP - 1]:
-                ptr, n = m.image_device_ptr(i)
-                reqs.append(dist.isend(torch.as_tensor(_DevView(ptr, n * 128), device=dev), rank - 1))
-        if halo_ids:
-            for k in range(len(halo_ids)):
-                reqs.append(dist.irecv(halo_buf[k * N_DESC:(k + 1) * N_DESC].view(-1), rank + 1))
-        for r in reqs:
-            r.wait()
+        def view(row):
+            ptr, n = m.image_device_ptr(row)
+            return torch.as_tensor(_DevView(ptr, n * 128), device=dev)
+        sharding.exchange_halo(sp, view, lambda row: halo_buf[row])
         torch.cuda.current_stream().synchronize()
-        for k, i in enumerate(halo_ids):
-            m.put_image_device(i, halo_buf[k * N_DESC:(k + 1) * N_DESC].data_ptr(), N_DESC)
+        for row in halo_ids:
+            m.put_image_device(row, halo_buf[row].data_ptr(), N_DESC)
 
     def barrier():
         if world > 1:
@@ -252,7 +247,7 @@ def run_ours(args):
     matches_per_step = 0
     for _ in range(args.warmup):
         matches_per_step = m.match_pairs_count(pairs)
-    sampler = ClockSampler(_physical_gpu_index(local))
+    sampler = ClockSampler(_physical_gpu_index(local), period=0.01)
     sampler.start()
     barrier()
     dev_ms, score_ms, launches, score_launches, ops = 0.0, 0.0, 0, 0, 0
@@ -260,16 +255,14 @@ def run_ours(args):
         flush_l2()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
+        # the halo (NCCL) is issued on torch's stream, the matcher runs on the library's stream: the first event
+        # goes where the step's first device work goes, the second after its last
+        e0.record(torch.cuda.current_stream() if world > 1 else stream)
         halo_exchange()
         m.match_pairs_count(pairs)
         e1.record(stream)
         e1.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        # device events bracket the call on the library's stream; the NCCL halo runs on torch's stream,
-        # so take the larger of the two clocks when a halo exists
-        step_ms = max(e0.elapsed_time(e1), wall if world > 1 else 0.0)
+        step_ms = e0.elapsed_time(e1)
         t = m.timing()
         dev_ms += step_ms
         score_ms += t["score_ms"]
@@ -346,14 +339,14 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"{IMAGES_PER_GPU} images x {N_DESC} descriptors per GPU, sequential overlap={OVERLAP}, "
-                            f"cross_check on (BASELINE.json configs[1]); {int(total_pairs)} pairs per step over {world} GPU(s)",
+                "workload": WORKLOAD,
                 "pairs_per_step": int(total_pairs), "matches_per_step_rank0": int(matches_per_step),
                 "l2": "flushed between timed steps (256 MiB write)",
                 "timing": "CUDA events on the library stream around the whole smb_match_pairs call (plan upload, kernels, "
                           "result copy); max over ranks",
-                "multi_gpu": "contiguous image windows, overlap-1 halo images received from the next rank over NCCL send/recv "
-                             "inside the timed step" if world > 1 else "single GPU",
+                "multi_gpu": "contiguous, cost-balanced image windows (sharding.plan); the overlap-1 halo images are received "
+                             "from the next rank's descriptor pool over NCCL send/recv inside every timed step; no "
+                             "other collective" if world > 1 else "single GPU",
             },
             "clocks": clocks,
             "e2e": {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
@@ -379,7 +372,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
