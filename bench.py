@@ -370,6 +370,7 @@ def run_ours(args):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)

@@ -75,13 +75,15 @@ def exchange_halo(p: ShardPlan, get_tensor: Callable[[int], "object"], make_recv
     return {row: received tensor}.  ``get_tensor(row)`` returns the tensor to send (a zero-copy view of the
     descriptor pool on GPUs); ``make_recv(row)`` allocates the receive buffer."""
     import torch.distributed as dist
-    reqs, out = [], {}
+    ops, out = [], {}
     for row, dst in p.send:
-        reqs.append(dist.isend(get_tensor(row), dst, group=group, tag=row))
+        ops.append(dist.P2POp(dist.isend, get_tensor(row), dst, group=group))
     for row, src in p.recv:
         buf = make_recv(row)
         out[row] = buf
-        reqs.append(dist.irecv(buf, src, group=group, tag=row))
-    for r in reqs:
-        r.wait()
+        ops.append(dist.P2POp(dist.irecv, buf, src, group=group))
+    if ops:
+        # one coalesced group: both sides list their ops in ascending row order per peer, so they pair up
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
     return out
