@@ -186,8 +186,10 @@ __device__ __forceinline__ void post_run(ScoreShared* sh, uint32_t e, uint32_t l
     const uint32_t posted = __ballot_sync(0xffffffffu, mine);
     head += __popc(posted);
     ballot &= ~posted;
-    fence_cta();
-    __syncwarp();
+    // No MEMBAR here (it would wait ~300+ clk for the vector stores above, on the tile pipeline's critical
+    // warp): the ballot is a warp barrier, so lane 0's store of the new head is issued after every lane's
+    // payload stores, and one warp's shared-memory stores are performed in issue order by the SM's single
+    // shared-memory pipe.  The consumer side pairs this with a fence after it has read the head.
     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = head;
   }
 }
