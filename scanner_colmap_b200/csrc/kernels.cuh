@@ -88,8 +88,9 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 //                 the accumulator buffer is released as soon as it has been read.  A run whose maximum
 //                 reaches min_score is copied, exact scores and all, from registers to a shared-memory
 //                 mailbox (a few vector stores; rare).
-//   warps 2,3     insert: lane l examines column l of every posted run and feeds scores >= min_score to
-//                 the top-2 accumulators (global atomics whose latency is off the tile pipeline).
+//   warps 2,3     insert: lane l examines column l of every posted run; scores >= min_score raise the best
+//                 keys with fire-and-forget RED.MAX and are appended to a survivor log, from which
+//                 runner_up_kernel settles the second-best keys afterwards.
 //
 // (A cta_group::2 variant -- CTA pairs sharing each B tile -- was built and measured slower on this
 // workload: with K = 128 the tile pipeline is bound by the accumulator hand-off latency, which the
@@ -108,7 +109,6 @@ constexpr int kScoreThreads = 32 * kScoreWarps;
 constexpr int kRunCols = 32;                   // accumulator columns per thread per tcgen05.ld
 constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 4, all in flight at once
 constexpr int kMailSlots = 16;                 // per epilogue warp: ring of survivor runs
-constexpr int kPostChunk = 8;                  // lanes of one warp that may post in one go (<= kMailSlots / 2)
 constexpr int kInsertBatch = 4;                // runs an insert warp handles per L2 round trip
 static_assert(kRunsPerWarp == 4, "epilogue code is written for four 32-column runs per warp");
 
@@ -161,50 +161,41 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Epilogue side (warp-uniform call).  Lanes whose run maximum reaches min_score copy the run (32 exact
-// scores, still in registers) into this warp's mailbox.  Single producer (this warp) / single consumer
-// (its insert warp): no atomics.  At most kPostChunk lanes post per round so a small ring cannot deadlock.
-__device__ __forceinline__ void post_run(ScoreShared* sh, uint32_t e, uint32_t lane, const uint32_t (&v)[32], bool hit,
-                                         uint32_t row_slot, uint32_t col_slot0, uint32_t& head) {
-  uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-  while (ballot) {
-    const uint32_t rank = __popc(ballot & ((1u << lane) - 1));
-    const bool mine = hit && rank < (uint32_t)kPostChunk;
-    if (mine) {
-      const uint32_t pos = head + rank;
-      uint32_t spins = 0;
-      while (pos - ld_volatile_shared(&sh->mail_tail[e]) >= (uint32_t)kMailSlots) {  // ring full: back-pressure
-        if (++spins > (1u << 28)) __trap();
-      }
-      const uint32_t dst = ptx::smem_u32(&sh->mail[e][pos % kMailSlots]);
-      st_shared_v4(dst, row_slot, col_slot0, 0u, 0u);
+// Copy one 32-column run (exact scores, still in registers) into a mailbox entry: 9 vector stores.
+__device__ __forceinline__ void store_run(ScoreShared* sh, uint32_t e, uint32_t pos, const uint32_t (&v)[32],
+                                          uint32_t row_slot, uint32_t col_slot0) {
+  const uint32_t dst = ptx::smem_u32(&sh->mail[e][pos % kMailSlots]);
+  st_shared_v4(dst, row_slot, col_slot0, 0u, 0u);
 #pragma unroll
-      for (int q = 0; q < kRunCols / 4; ++q)
-        st_shared_v4(dst + 16 + q * 16, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      hit = false;
-    }
-    const uint32_t posted = __ballot_sync(0xffffffffu, mine);
-    head += __popc(posted);
-    ballot &= ~posted;
-    // No MEMBAR here (it would wait ~300+ clk for the vector stores above, on the tile pipeline's critical
-    // warp): the ballot is a warp barrier, so lane 0's store of the new head is issued after every lane's
-    // payload stores, and one warp's shared-memory stores are performed in issue order by the SM's single
-    // shared-memory pipe.  The consumer side pairs this with a fence after it has read the head.
-    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = head;
-  }
+  for (int q = 0; q < kRunCols / 4; ++q) st_shared_v4(dst + 16 + q * 16, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// Survivor log: with `log` != nullptr the insert warps never wait for an atomic.  They raise the best keys with
+// fire-and-forget RED.MAX and append {row slot, column slot, score} to a global log; runner_up_kernel then
+// offers every logged survivor that is not the final best to the runner-up keys.  The log is written in
+// per-warp chunks (one returning atomic per kLogChunk survivors); unused chunk tails are zero-filled.  If the
+// log overflows (adversarial inputs where almost every score survives) the host repeats the batch with
+// log == nullptr, where every insertion uses the returning two-stage top2_insert2.
+constexpr uint32_t kLogChunk = 256;
+
+struct SurvivorLog {
+  uint4* entries;               // {row slot, column slot, score, 0}; score 0 = unused
+  unsigned long long* count;    // entries reserved so far (may exceed capacity: overflow)
+  unsigned long long capacity;
+};
+
 // Insert warp r serves the mailboxes of epilogue warps r, r + 2, r + 4, r + 6.  Lane l looks at column
-// (run + l) of every run: a score >= min_score is a survivor and goes to the top-2 accumulators of its row
-// and its column.  Up to kInsertBatch runs are taken per pass and their survivors are compacted onto
-// consecutive lanes, so all insertions of a pass share one L2 round trip.
-__device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict__ acc, int min_score,
+// (run + l) of every run: a score >= min_score is a survivor of its row and its column.  Up to kInsertBatch
+// runs are taken per pass and their survivors are compacted onto consecutive lanes.
+__device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict__ acc, SurvivorLog slog, int min_score,
                                             uint32_t r, uint32_t lane, unsigned long long* cand_counter, uint32_t dbg) {
   constexpr int kBoxes = kEpiWarps / kInsertWarps;
   uint32_t tail[kBoxes];
 #pragma unroll
   for (int k = 0; k < kBoxes; ++k) tail[k] = 0;
   uint32_t count = 0;
+  unsigned long long chunk_pos = 0;  // next free entry of this warp's current log chunk
+  uint32_t chunk_left = 0;
   for (;;) {
     uint32_t row_slot[kInsertBatch], col_slot[kInsertBatch], sc[kInsertBatch];
     uint32_t got = 0;
@@ -257,15 +248,33 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
             st_shared_v4(ptx::smem_u32(&sh->jobs[r][job - base]), row_slot[b], col_slot[b], sc[b], 0u);
         }
         __syncwarp();
-        if (base + lane < total) {
-          uint32_t jr, jc, js, jp;
+        const uint32_t njobs = total - base < 32u ? total - base : 32u;
+        uint32_t jr = 0, jc = 0, js = 0, jp = 0;
+        if (lane < njobs)
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(jr), "=r"(jc), "=r"(js), "=r"(jp)
                        : "r"(ptx::smem_u32(&sh->jobs[r][lane]))
                        : "memory");
+        if (slog.entries) {
+          if (chunk_left < njobs) {  // warp-uniform: retire the chunk (zero its tail) and reserve a new one
+            for (uint32_t x = lane; x < chunk_left; x += 32)
+              if (chunk_pos + x < slog.capacity) slog.entries[chunk_pos + x] = make_uint4(0, 0, 0, 0);
+            unsigned long long p = 0;
+            if (lane == 0) p = atomicAdd(slog.count, (unsigned long long)kLogChunk);
+            chunk_pos = __shfl_sync(0xffffffffu, p, 0);
+            chunk_left = kLogChunk;
+          }
+          if (lane < njobs) {
+            atomicMax(&acc[jr].k1, make_key(js, jc));  // results unused: RED, nothing to wait for
+            atomicMax(&acc[jc].k1, make_key(js, jr));
+            if (chunk_pos + lane < slog.capacity) slog.entries[chunk_pos + lane] = make_uint4(jr, jc, js, 0u);
+          }
+          chunk_pos += njobs;
+          chunk_left -= njobs;
+        } else if (lane < njobs) {
           top2_insert2(acc, jr, jc, js);
-          ++count;
         }
+        count += lane < njobs;
         __syncwarp();
       }
     } else {
@@ -281,12 +290,35 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
       }
     }
   }
+  if (slog.entries)
+    for (uint32_t x = lane; x < chunk_left; x += 32)
+      if (chunk_pos + x < slog.capacity) slog.entries[chunk_pos + x] = make_uint4(0, 0, 0, 0);
   if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
+}
+
+// Second stage of the logged insertion: every survivor that is not the final best of its row (column)
+// competes for that row's (column's) runner-up key.  Keys are distinct, so "not the best" == "key != k1".
+__global__ void __launch_bounds__(256)
+runner_up_kernel(const uint4* __restrict__ entries, const unsigned long long* __restrict__ count,
+                 unsigned long long* __restrict__ overflow_flag, unsigned long long capacity, TopTwo* __restrict__ acc) {
+  unsigned long long n = *count;
+  if (n > capacity) {  // overflow: the host discards this attempt and repeats it without the log
+    if (blockIdx.x == 0 && threadIdx.x == 0) *overflow_flag = 1ull;
+    n = capacity;
+  }
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 e = entries[i];
+    if (e.z == 0) continue;
+    const unsigned long long kr = make_key(e.z, e.y), kc = make_key(e.z, e.x);
+    if (acc[e.x].k1 != kr) atomicMax(&acc[e.x].k2, kr);
+    if (acc[e.y].k1 != kc) atomicMax(&acc[e.y].k2, kc);
+  }
 }
 
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
-                     const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, int min_score,
+                     const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, SurvivorLog slog, int min_score,
                      unsigned long long* cand_counter, uint32_t dbg) {
   // dbg (bring-up timing experiments only, results become meaningless):
   // 2 = B tiles are not loaded, 4 = survivor runs are not posted, 8 = survivors are not inserted
@@ -393,7 +425,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are visible to this warp
     const uint32_t col0 = (e >> 2) * kEpiCols;  // which 128 of the tile's 256 columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
-    uint32_t ts = 0, tph = 0, mail_head = 0;
+    uint32_t ts = 0, tph = 0, mail_head = 0, mail_tail_seen = 0;
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairMeta pm = pairs[w.pair];
@@ -417,14 +449,46 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
-          if (__any_sync(0xffffffffu, max(max(mc0, mc1), max(mc2, mc3)) >= min_score) && !(dbg & 4)) {
-            // rare: some run holds a survivor; the lanes concerned hand the run to the insert warps.
-            // Pool padding rows are all-zero descriptors (score 0 < min_score), so no bounds test is needed.
+          // Which of this thread's four runs hold a survivor (rare).  One ballot for the whole warp; the few
+          // lanes concerned are then served one after the other with warp-uniform control flow, so the common
+          // case (one lane, one run) costs a ballot, a shuffle and nine vector stores.  Single producer (this
+          // warp) / single consumer (its insert warp) ring: no atomics; the consumer's tail is re-read only
+          // when the cached copy says the ring is full.  Pool padding rows are all-zero descriptors
+          // (score 0 < min_score), so no bounds test is needed.
+          const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
+                              (mc3 >= min_score ? 8u : 0u);
+          uint32_t lanes = __ballot_sync(0xffffffffu, hm != 0);
+          if (lanes && !(dbg & 4)) {
             const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
-            post_run(sh, e, lane, v0, mc0 >= min_score, rslot, cslot, mail_head);
-            post_run(sh, e, lane, v1, mc1 >= min_score, rslot, cslot + kRunCols, mail_head);
-            post_run(sh, e, lane, v2, mc2 >= min_score, rslot, cslot + 2 * kRunCols, mail_head);
-            post_run(sh, e, lane, v3, mc3 >= min_score, rslot, cslot + 3 * kRunCols, mail_head);
+            do {
+              const int src = __ffs(lanes) - 1;
+              lanes &= lanes - 1;
+              const uint32_t m = __shfl_sync(0xffffffffu, hm, src);
+              const uint32_t need = __popc(m);
+              if (mail_head + need - mail_tail_seen > (uint32_t)kMailSlots) {  // ring (seems) full: back-pressure
+                __syncwarp();  // publish what has been written so far, or the consumer could never make room
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = mail_head;
+                uint32_t spins = 0;
+                do {
+                  mail_tail_seen = ld_volatile_shared(&sh->mail_tail[e]);
+                  if (++spins > (1u << 28)) __trap();
+                } while (mail_head + need - mail_tail_seen > (uint32_t)kMailSlots);
+              }
+              if (lane == (uint32_t)src) {
+                uint32_t pos = mail_head;
+                if (m & 1u) store_run(sh, e, pos++, v0, rslot, cslot);
+                if (m & 2u) store_run(sh, e, pos++, v1, rslot, cslot + kRunCols);
+                if (m & 4u) store_run(sh, e, pos++, v2, rslot, cslot + 2 * kRunCols);
+                if (m & 8u) store_run(sh, e, pos++, v3, rslot, cslot + 3 * kRunCols);
+              }
+              mail_head += need;
+            } while (lanes);
+            // No MEMBAR (it would wait ~300+ clk for the vector stores above, on the tile pipeline's critical
+            // warp): __syncwarp orders the lanes, so lane 0's store of the new head is issued after every
+            // lane's payload stores, and one warp's shared-memory stores are performed in issue order by the
+            // SM's single shared-memory pipe.  The consumer pairs this with a fence after reading the head.
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = mail_head;
           }
         }
       }
@@ -436,7 +500,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     }
   } else {
     // ------------------------------------------------------------ insert (warps 2, 3)
-    insert_loop(sh, acc, min_score, warp - 2, lane, cand_counter, dbg);
+    insert_loop(sh, acc, slog, min_score, warp - 2, lane, cand_counter, dbg);
   }
 
   ptx::tcgen05_fence_before();

@@ -126,11 +126,13 @@ struct smb_handle {
   DevBuf<TopTwo> d_acc;
   DevBuf<uint2> d_out;
   DevBuf<PairOut> d_pair_out;
-  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates
+  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed
+  DevBuf<uint4> d_log;                       // survivor log (kernels.cuh SurvivorLog)
+  size_t log_cap = (size_t)16 << 20;         // entries; SMB_LOG_CAP overrides (tests force the overflow path)
   PinnedBuf<PairMeta> h_pairs;
   PinnedBuf<WorkItem> h_items;
   PinnedBuf<PairOut> h_pair_out;
-  unsigned long long* h_counters = nullptr;  // pinned [2]
+  unsigned long long* h_counters = nullptr;  // pinned [4]
 
   std::vector<smb_result*> result_pool;
   smb_timing timing{};
@@ -371,6 +373,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->device = cuda_device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
+  if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
   int rc = SMB_OK;
   auto bail = [&](int code) {
     g_create_error = h->err;
@@ -406,8 +409,8 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   }
   SMB_CUDA_C(cudaMalloc(&h->lut_dev, kLutSize * sizeof(float)));
   SMB_CUDA_C(cudaMemcpyAsync(h->lut_dev, h->lut_host.data(), kLutSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  SMB_CUDA_C(cudaMalloc(&h->d_counters, 2 * sizeof(unsigned long long)));
-  SMB_CUDA_C(cudaMallocHost(&h->h_counters, 2 * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMallocHost(&h->h_counters, 4 * sizeof(unsigned long long)));
   SMB_CUDA_C(cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
   SMB_CUDA_C(cudaStreamSynchronize(h->stream));
 #undef SMB_CUDA_C
@@ -432,6 +435,7 @@ void smb_destroy(smb_handle* h) {
   h->d_acc.release();
   h->d_out.release();
   h->d_pair_out.release();
+  h->d_log.release();
   h->h_pairs.release();
   h->h_items.release();
   h->h_pair_out.release();
@@ -514,7 +518,9 @@ int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** de
   return SMB_OK;
 }
 
-static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, size_t npairs, smb_result** out) {
+static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */, size_t npairs, smb_result** out,
+                           bool use_log, bool* overflowed) {
+  *overflowed = false;
   *out = nullptr;
   SMB_CUDA(h, cudaSetDevice(h->device));
   const bool prof = h->opts.profile != 0;
@@ -580,7 +586,8 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
   if (cudaSuccess != h->d_pairs.reserve(max_pairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(max_items, 1)) ||
       cudaSuccess != h->d_acc.reserve(std::max<size_t>(max_acc, 1)) || cudaSuccess != h->d_out.reserve(std::max<size_t>(out_cap, 1)) ||
       cudaSuccess != h->d_pair_out.reserve(npairs) || cudaSuccess != h->h_pair_out.reserve(npairs) ||
-      cudaSuccess != h->h_items.reserve(std::max<size_t>(max_items, 1))) {
+      cudaSuccess != h->h_items.reserve(std::max<size_t>(max_items, 1)) ||
+      (use_log && h->log_cap && cudaSuccess != h->d_log.reserve(h->log_cap))) {
     cudaGetLastError();
     return give_back(fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu out=%zu)", npairs,
                           max_acc, out_cap));
@@ -595,7 +602,9 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
   } while (0)
 
   if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
-  SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned long long), st));
+  SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  use_log = use_log && h->log_cap && h->opts.engine == SMB_ENGINE_TCGEN05;
+  const SurvivorLog slog{use_log ? h->d_log.p : nullptr, h->d_counters + 2, (unsigned long long)h->log_cap};
   float score_ms = 0.f, decide_ms = 0.f;
   uint64_t ops = 0;
 
@@ -627,9 +636,16 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
       if (h->opts.engine == SMB_ENGINE_TCGEN05) {
         if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
+        if (use_log) SMB_CUDA_R(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), st));
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);  // persistent CTAs
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
-                                                                          h->d_acc.p, h->filter.min_score, cand, h->dbg_flags);
+                                                                          h->d_acc.p, slog, h->filter.min_score, cand, h->dbg_flags);
+        if (use_log) {
+          SMB_CUDA_R(cudaGetLastError());
+          runner_up_kernel<<<(unsigned)h->num_sms * 8, 256, 0, st>>>(h->d_log.p, h->d_counters + 2, h->d_counters + 3,
+                                                                    (unsigned long long)h->log_cap, h->d_acc.p);
+          h->timing.total_launches++;
+        }
       } else {
         const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
         score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p, h->d_acc.p,
@@ -664,8 +680,12 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
 
   // ---- results: header first (sizes), then exactly the matches that exist
   SMB_CUDA_R(cudaMemcpyAsync(h->h_pair_out.p, h->d_pair_out.p, npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
-  SMB_CUDA_R(cudaMemcpyAsync(h->h_counters, h->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  SMB_CUDA_R(cudaMemcpyAsync(h->h_counters, h->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   SMB_CUDA_R(cudaStreamSynchronize(st));
+  if (h->h_counters[3]) {  // the survivor log overflowed: this attempt's runner-up keys are incomplete
+    *overflowed = true;
+    return give_back(SMB_OK);
+  }
   const size_t total = (size_t)h->h_counters[0];
   if (total > out_cap) return give_back(fail(h, SMB_ECUDA, "internal error: %zu matches exceed capacity %zu", total, out_cap));
   if (total > res->matches_cap) {
@@ -695,6 +715,13 @@ static int match_keys(smb_handle* h, const uint64_t* keys /* [npairs][2] */, siz
 #undef SMB_CUDA_R
   *out = res;
   return SMB_OK;
+}
+
+static int match_keys(smb_handle* h, const uint64_t* keys, size_t npairs, smb_result** out) {
+  bool overflowed = false;
+  int rc = match_keys_impl(h, keys, npairs, out, /*use_log=*/true, &overflowed);
+  if (rc == SMB_OK && overflowed) rc = match_keys_impl(h, keys, npairs, out, /*use_log=*/false, &overflowed);  // exact, slower
+  return rc;
 }
 
 int smb_match_pairs(smb_handle* h, const uint32_t* pairs, size_t npairs, smb_result** out) {

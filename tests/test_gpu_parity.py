@@ -173,3 +173,21 @@ def test_full_size_properties_8192():
     assert np.all(np.diff(ab[:, 0].astype(np.int64)) > 0)  # ascending idx1, unique
     assert len(np.unique(ab[:, 1])) == len(ab)    # one-to-one
     assert np.array_equal(aa[:, 0], aa[:, 1])     # an image matched with itself pairs each row with itself
+
+
+def test_survivor_log_overflow_falls_back_exactly(oracle, monkeypatch):
+    """With a tiny survivor log the fast (fire-and-forget) insertion overflows and the batch is repeated with
+    returning atomics; results must not change.  Also exercises log chunks straddling the capacity."""
+    a = synth.make_image(20, 1500, track_step=32)
+    b = synth.make_image(21, 1400, track_step=32)
+    want = oracle.match(a, b)
+    assert len(want) > 300
+    for cap in ("0", "256", "700"):
+        monkeypatch.setenv("SMB_LOG_CAP", cap)
+        with SiftMatcher() as m:
+            assert np.array_equal(m.match(a, b), want), f"SMB_LOG_CAP={cap}"
+    monkeypatch.delenv("SMB_LOG_CAP")
+    dense_a = np.tile(a[:1], (300, 1))
+    with SiftMatcher(max_ratio=1.1, max_distance=2.0, cross_check=False) as m:   # every score survives: 90k log entries
+        got = m.match(dense_a, b)
+    assert np.array_equal(got, oracle.match(dense_a, b, max_ratio=1.1, max_distance=2.0, cross_check=False))
