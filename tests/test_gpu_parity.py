@@ -191,3 +191,46 @@ def test_survivor_log_overflow_falls_back_exactly(oracle, monkeypatch):
     with SiftMatcher(max_ratio=1.1, max_distance=2.0, cross_check=False) as m:   # every score survives: 90k log entries
         got = m.match(dense_a, b)
     assert np.array_equal(got, oracle.match(dense_a, b, max_ratio=1.1, max_distance=2.0, cross_check=False))
+
+
+def test_ragged_video_set_reduced(oracle):
+    """BASELINE.json configs[3] (ragged 1k-16k descriptors per image, overlap 10) at 1/8 of the sizes so the
+    CPU oracle finishes in seconds: every pair of a 24-image window set, bit-exact."""
+    sizes = (synth.ragged_sizes(24, lo=128, hi=2048, seed=99)).tolist()
+    ids = list(range(500, 524))
+    imgs = [synth.make_image(i, n, track_step=24) for i, n in zip(ids, sizes)]
+    pairs = sequential_pairs(ids, 10)
+    with SiftMatcher() as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+    assert total > 500 and min(sizes) < 300 and max(sizes) > 1500
+
+
+def test_exhaustive_pairs_reduced(oracle):
+    """BASELINE.json configs[4] (exhaustive matching) reduced to 12 images x 640 descriptors: all 66 pairs."""
+    ids = list(range(12))
+    imgs = [synth.make_image(i, 640, track_step=40) for i in ids]
+    pairs = np.array([(a, b) for a in ids for b in ids if a < b], dtype=np.uint32)
+    with SiftMatcher(max_num_matches=32768) as m:
+        m.put_images(ids, imgs)
+        _check_pairs(oracle, m, imgs, ids, pairs)
+
+
+def test_full_size_ragged_properties():
+    """Ragged full-size images (up to 16384 descriptors) through size-independent properties."""
+    sizes = [16384, 1024, 5000, 9999]
+    imgs = [synth.make_image(i, n) for i, n in enumerate(sizes)]
+    prs = np.array([[0, 1], [1, 0], [0, 2], [2, 0], [2, 3], [3, 2], [0, 3], [0, 0]], dtype=np.uint32)
+    with SiftMatcher() as m:
+        m.put_images(range(4), imgs)
+        res = m.match_pairs(prs)
+        res2 = m.match_pairs(prs)
+    for a, b in zip(res, res2):
+        assert np.array_equal(a, b)
+    for k in (0, 2, 4):
+        ab, ba = res[k], res[k + 1][:, ::-1]
+        ba = ba[np.argsort(ba[:, 0], kind="stable")]
+        assert np.array_equal(ab, ba)
+        n1, n2 = sizes[prs[k][0]], sizes[prs[k][1]]
+        assert (ab[:, 0] < n1).all() and (ab[:, 1] < n2).all()
+    assert len(res[0]) > 50 and np.array_equal(res[7][:, 0], res[7][:, 1])
