@@ -74,8 +74,8 @@ typedef struct smb_result smb_result;
  * handle's stream; valid only when options.profile != 0). */
 typedef struct smb_timing {
   float total_ms;       /* first upload to last device->host copy */
-  float score_ms;       /* the dot-product + filter kernel(s) only (summed over internal batches) */
-  float decide_ms;      /* top-2 resolve + tests + cross-check + compaction kernels */
+  float score_ms;       /* the score (+ runner-up) kernels only, summed over the call's sub-batches */
+  float decide_ms;      /* reserved (0): the decide kernels run on a second stream under the next sub-batch's scoring */
   uint32_t score_launches;
   uint32_t total_launches; /* every kernel of this library launched by the call */
   uint64_t candidates;  /* score-matrix entries that survived the integer pre-filter */

@@ -105,7 +105,9 @@ struct smb_handle {
   float max_ratio_f = 0.f, max_distance_f = 0.f;
   Filter filter{};
   std::string err;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // uploads, accumulator clears, score kernels
+  cudaStream_t stream_out = nullptr;  // decide kernels and result copies (overlap the next sub-batch's scoring)
+  std::vector<cudaEvent_t> ev_pool;   // 4 per sub-batch: scored, decided, score begin/end
   cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
 
   // descriptor pool
@@ -132,6 +134,7 @@ struct smb_handle {
   PinnedBuf<PairMeta> h_pairs;
   PinnedBuf<WorkItem> h_items;
   PinnedBuf<PairOut> h_pair_out;
+  PinnedBuf<unsigned long long> h_sub_counters;  // device counters as seen after each sub-batch
   unsigned long long* h_counters = nullptr;  // pinned [4]
 
   std::vector<smb_result*> result_pool;
@@ -374,6 +377,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
+  if (const char* e = getenv("SMB_ACC_BUDGET")) h->acc_budget = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 0));  // tests: force sub-batches
   int rc = SMB_OK;
   auto bail = [&](int code) {
     g_create_error = h->err;
@@ -390,6 +394,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   } while (0)
   SMB_CUDA_C(cudaSetDevice(cuda_device));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
   for (auto& e : h->ev) SMB_CUDA_C(cudaEventCreate(&e));
   {
     void* fn = nullptr;
@@ -426,6 +431,7 @@ void smb_destroy(smb_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_out) cudaStreamSynchronize(h->stream_out);
   for (smb_result* r : h->result_pool) {
     if (r->matches) cudaFreeHost(r->matches);
     delete r;
@@ -439,6 +445,8 @@ void smb_destroy(smb_handle* h) {
   h->h_pairs.release();
   h->h_items.release();
   h->h_pair_out.release();
+  h->h_sub_counters.release();
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->lut_dev) cudaFree(h->lut_dev);
@@ -446,6 +454,7 @@ void smb_destroy(smb_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream_out) cudaStreamDestroy(h->stream_out);
   delete h;
 }
 
@@ -518,6 +527,12 @@ int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** de
   return SMB_OK;
 }
 
+// One smb_match_pairs call.  The pair list is cut into a few sub-batches that flow through two streams:
+//   main stream : [plan upload] -> per sub-batch: zero the accumulators, score (+ runner-up) and decide kernels
+//   out  stream : per sub-batch, once decided: header copy, then exactly its matches -> pinned host memory
+// so the result copies of sub-batch k run on the copy engine under the scoring of sub-batch k+1.  (Running
+// the decide kernels on the second stream as well was measured slower: the persistent score CTAs own every
+// SM, so a concurrent decide kernel only delays the next score kernel's CTAs.)
 static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */, size_t npairs, smb_result** out,
                            bool use_log, bool* overflowed) {
   *overflowed = false;
@@ -541,13 +556,19 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   }
   if (npairs > 0x7FFFFFFFull) return give_back(fail(h, SMB_EINVAL, "too many pairs in one call"));
 
-  // ---- plan: metas, output capacity, internal batches bounded by the accumulator budget
-  int rc = SMB_OK;
+  // ---- plan: metas, work items, sub-batches
+  struct Sub { size_t first, last, item0, items, acc, out_cap; };
+  std::vector<Sub> subs;
   if (cudaSuccess != h->h_pairs.reserve(npairs)) return give_back(fail(h, SMB_ENOMEM, "pinned allocation failed"));
-  std::vector<BatchPlan> batches;
-  size_t out_cap = 0, n_items_total = 0, max_items = 0, max_acc = 0, max_pairs = 0;
+  // Sub-batches exist to bound the accumulator footprint.  Splitting further to overlap result copies with
+  // scoring was measured slower (855 pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score
+  // launch pays its own tail), so a call is one sub-batch unless the accumulator budget says otherwise.
+  const size_t target_pairs = npairs;
+  const size_t sub_budget = h->acc_budget;
+  size_t out_cap = 0, n_items_total = 0, max_acc = 0;
+  uint64_t ops = 0;
   {
-    size_t b_first = 0, b_acc = 0, b_items = 0;
+    Sub cur{0, 0, 0, 0, 0, 0};
     for (size_t p = 0; p < npairs; ++p) {
       auto i1 = h->images.find(keys[2 * p]);
       auto i2 = h->images.find(keys[2 * p + 1]);
@@ -556,162 +577,195 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
                               (unsigned long long)(i1 == h->images.end() ? keys[2 * p] : keys[2 * p + 1])));
       const ImageEntry &a = i1->second, &b = i2->second;
       const size_t need = (size_t)a.n + b.n;
-      if (p > b_first && b_acc + need > h->acc_budget) {
-        batches.push_back({b_first, p});
-        max_items = std::max(max_items, b_items);
-        max_acc = std::max(max_acc, b_acc);
-        max_pairs = std::max(max_pairs, p - b_first);
-        b_first = p;
-        b_acc = 0;
-        b_items = 0;
+      if (p > cur.first && (cur.acc + need > sub_budget || p - cur.first >= target_pairs)) {
+        cur.last = p;
+        subs.push_back(cur);
+        cur = Sub{p, 0, cur.item0 + cur.items, 0, 0, 0};
       }
       PairMeta& m = h->h_pairs.p[p];
       m.a_row0 = a.row0;
       m.n1 = a.n;
       m.b_row0 = b.row0;
       m.n2 = b.n;
-      m.acc_off = (uint32_t)b_acc;
+      m.acc_off = (uint32_t)cur.acc;
       m.out_slot = (uint32_t)p;
-      b_acc += need;
-      if (a.n && b.n) b_items += (a.n + kStripRows - 1) / kStripRows;
-      out_cap += cc ? std::min(a.n, b.n) : a.n;
+      cur.acc += need;
+      if (a.n && b.n) cur.items += (a.n + kStripRows - 1) / kStripRows;
+      cur.out_cap += cc ? std::min(a.n, b.n) : a.n;
+      ops += 2ull * a.n * b.n * kDim;
     }
-    batches.push_back({b_first, npairs});
-    max_items = std::max(max_items, b_items);
-    max_acc = std::max(max_acc, b_acc);
-    max_pairs = std::max(max_pairs, npairs - b_first);
+    cur.last = npairs;
+    subs.push_back(cur);
+    for (const Sub& sb : subs) {
+      n_items_total += sb.items;
+      max_acc = std::max(max_acc, sb.acc);
+      out_cap += sb.out_cap;
+    }
   }
   if (out_cap > 0xFFFFFFFFull) return give_back(fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call"));
+  const size_t acc_region = (max_acc + 15) / 16 * 16;
+  use_log = use_log && h->log_cap && h->opts.engine == SMB_ENGINE_TCGEN05;
 
-  if (cudaSuccess != h->d_pairs.reserve(max_pairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(max_items, 1)) ||
-      cudaSuccess != h->d_acc.reserve(std::max<size_t>(max_acc, 1)) || cudaSuccess != h->d_out.reserve(std::max<size_t>(out_cap, 1)) ||
-      cudaSuccess != h->d_pair_out.reserve(npairs) || cudaSuccess != h->h_pair_out.reserve(npairs) ||
-      cudaSuccess != h->h_items.reserve(std::max<size_t>(max_items, 1)) ||
-      (use_log && h->log_cap && cudaSuccess != h->d_log.reserve(h->log_cap))) {
+  if (cudaSuccess != h->d_pairs.reserve(npairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(n_items_total, 1)) ||
+      cudaSuccess != h->d_acc.reserve(std::max<size_t>(acc_region, 1)) ||
+      cudaSuccess != h->d_out.reserve(std::max<size_t>(out_cap, 1)) || cudaSuccess != h->d_pair_out.reserve(npairs) ||
+      cudaSuccess != h->h_pair_out.reserve(npairs) || cudaSuccess != h->h_items.reserve(std::max<size_t>(n_items_total, 1)) ||
+      cudaSuccess != h->h_sub_counters.reserve(4 * subs.size()) ||
+      (use_log && cudaSuccess != h->d_log.reserve(h->log_cap))) {
     cudaGetLastError();
     return give_back(fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu out=%zu)", npairs,
-                          max_acc, out_cap));
+                          acc_region, out_cap));
+  }
+  // pinned result buffer: starts at a quarter of the worst case (min(n1, n2) matches per pair), grown on demand
+  auto ensure_matches = [&](size_t need, size_t keep) -> bool {
+    if (need <= res->matches_cap) return true;
+    const size_t want = std::max<size_t>(std::max(need, res->matches_cap * 2), 4096);
+    smb_match* q = nullptr;
+    if (cudaMallocHost(&q, want * sizeof(smb_match)) != cudaSuccess) return false;
+    if (res->matches) {
+      if (keep) std::memcpy(q, res->matches, keep * sizeof(smb_match));
+      cudaFreeHost(res->matches);
+    }
+    res->matches = q;
+    res->matches_cap = want;
+    return true;
+  };
+  if (!ensure_matches(out_cap / 4 + 1, 0)) return give_back(fail(h, SMB_ENOMEM, "pinned result allocation failed"));
+  while (h->ev_pool.size() < 4 * subs.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return give_back(fail(h, SMB_ECUDA, "cudaEventCreate failed"));
+    h->ev_pool.push_back(e);
   }
 
-  cudaStream_t st = h->stream;
+  // work items: one per 256-row strip, pairs in caller order (strips of a pair stay adjacent so concurrently
+  // running CTAs stream the same image 2 out of L2), largest column counts first inside each sub-batch
+  for (const Sub& sb : subs) {
+    WorkItem* it0 = h->h_items.p + sb.item0;
+    size_t ni = 0;
+    for (size_t p = sb.first; p < sb.last; ++p) {
+      const PairMeta& m = h->h_pairs.p[p];
+      if (!m.n1 || !m.n2) continue;
+      const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
+      for (uint32_t r = 0; r < m.n1; r += kStripRows)
+        it0[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - sb.first), m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
+    }
+    bool uniform = true;
+    for (size_t x = 1; x < ni && uniform; ++x) uniform = it0[x].n_btiles == it0[0].n_btiles;
+    if (!uniform) std::stable_sort(it0, it0 + ni, [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
+  }
+
+  cudaStream_t st = h->stream, so = h->stream_out;
 #define SMB_CUDA_R(expr)                                                                                  \
   do {                                                                                                    \
     cudaError_t e__ = (expr);                                                                             \
-    if (e__ != cudaSuccess)                                                                               \
+    if (e__ != cudaSuccess) {                                                                             \
+      cudaStreamSynchronize(st);                                                                          \
+      cudaStreamSynchronize(so);                                                                          \
       return give_back(fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    }                                                                                                     \
   } while (0)
 
   if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
   SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  use_log = use_log && h->log_cap && h->opts.engine == SMB_ENGINE_TCGEN05;
+  SMB_CUDA_R(cudaMemcpyAsync(h->d_pairs.p, h->h_pairs.p, npairs * sizeof(PairMeta), cudaMemcpyHostToDevice, st));
+  if (n_items_total)
+    SMB_CUDA_R(cudaMemcpyAsync(h->d_items.p, h->h_items.p, n_items_total * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
   const SurvivorLog slog{use_log ? h->d_log.p : nullptr, h->d_counters + 2, (unsigned long long)h->log_cap};
-  float score_ms = 0.f, decide_ms = 0.f;
-  uint64_t ops = 0;
+  if (h->opts.engine == SMB_ENGINE_TCGEN05 && n_items_total && !h->tmap_valid)
+    return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
 
-  for (const BatchPlan& bp : batches) {
-    const size_t np = bp.last - bp.first;
-    // work items: one per 128-row strip, pairs in caller order (strips of a pair stay adjacent so
-    // concurrently running CTAs stream the same image 2 out of L2), largest column counts first
-    size_t ni = 0, acc_entries = 0;
-    for (size_t p = bp.first; p < bp.last; ++p) {
-      const PairMeta& m = h->h_pairs.p[p];
-      acc_entries += (size_t)m.n1 + m.n2;
-      ops += 2ull * m.n1 * m.n2 * kDim;
-      if (!m.n1 || !m.n2) continue;
-      const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
-      for (uint32_t r = 0; r < m.n1; r += kStripRows)
-        h->h_items.p[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - bp.first),
-                                      m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
-    }
-    std::stable_sort(h->h_items.p, h->h_items.p + ni,
-                     [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
-    n_items_total += ni;
-
-    SMB_CUDA_R(cudaMemcpyAsync(h->d_pairs.p, h->h_pairs.p + bp.first, np * sizeof(PairMeta), cudaMemcpyHostToDevice, st));
-    if (ni) SMB_CUDA_R(cudaMemcpyAsync(h->d_items.p, h->h_items.p, ni * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
-    if (acc_entries) SMB_CUDA_R(cudaMemsetAsync(h->d_acc.p, 0, acc_entries * sizeof(TopTwo), st));
-
-    if (ni) {
-      if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[2], st));
+  for (size_t k = 0; k < subs.size(); ++k) {
+    const Sub& sb = subs[k];
+    cudaEvent_t ev_scored = h->ev_pool[4 * k], ev_decided = h->ev_pool[4 * k + 1], ev_s0 = h->ev_pool[4 * k + 2],
+                ev_s1 = h->ev_pool[4 * k + 3];
+    TopTwo* acc = h->d_acc.p;  // reused by every sub-batch: all kernels touching it are ordered on the main stream
+    if (sb.acc) SMB_CUDA_R(cudaMemsetAsync(acc, 0, sb.acc * sizeof(TopTwo), st));
+    if (sb.items) {
+      if (prof) SMB_CUDA_R(cudaEventRecord(ev_s0, st));
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
       if (h->opts.engine == SMB_ENGINE_TCGEN05) {
-        if (!h->tmap_valid) return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
         if (use_log) SMB_CUDA_R(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), st));
-        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms);  // persistent CTAs
-        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p, (uint32_t)ni, h->d_pairs.p,
-                                                                          h->d_acc.p, slog, h->filter.min_score, cand, h->dbg_flags);
+        const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms);  // persistent CTAs
+        score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p + sb.item0, (uint32_t)sb.items,
+                                                                          h->d_pairs.p + sb.first, acc, slog,
+                                                                          h->filter.min_score, cand, h->dbg_flags);
         if (use_log) {
           SMB_CUDA_R(cudaGetLastError());
           runner_up_kernel<<<(unsigned)h->num_sms * 8, 256, 0, st>>>(h->d_log.p, h->d_counters + 2, h->d_counters + 3,
-                                                                    (unsigned long long)h->log_cap, h->d_acc.p);
+                                                                    (unsigned long long)h->log_cap, acc);
           h->timing.total_launches++;
         }
       } else {
-        const unsigned grid = (unsigned)std::min<size_t>(ni, (size_t)h->num_sms * 4);
-        score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p, (uint32_t)ni, h->d_pairs.p, h->d_acc.p,
-                                                         h->filter.min_score, cand);
+        const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms * 4);
+        score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p + sb.item0, (uint32_t)sb.items,
+                                                         h->d_pairs.p + sb.first, acc, h->filter.min_score, cand);
       }
       SMB_CUDA_R(cudaGetLastError());
       h->timing.score_launches++;
       h->timing.total_launches++;
-      if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[3], st));
+      if (prof) SMB_CUDA_R(cudaEventRecord(ev_s1, st));
     }
-    if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[4], st));
-    decide_kernel<<<(unsigned)np, kDecideThreads, 0, st>>>(h->d_pairs.p, h->d_acc.p, h->lut_dev, h->max_ratio_f,
-                                                          h->max_distance_f, cc ? 1 : 0, h->d_out.p, h->d_counters,
-                                                          h->d_pair_out.p);
+    decide_kernel<<<(unsigned)(sb.last - sb.first), kDecideThreads, 0, st>>>(h->d_pairs.p + sb.first, acc, h->lut_dev,
+                                                                             h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
+                                                                             h->d_out.p, h->d_counters, h->d_pair_out.p);
     SMB_CUDA_R(cudaGetLastError());
     h->timing.total_launches++;
-    if (prof) {
-      SMB_CUDA_R(cudaEventRecord(h->ev[5], st));
-      SMB_CUDA_R(cudaEventSynchronize(h->ev[5]));
-      float ms = 0.f;
-      if (ni) {
-        SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
-        score_ms += ms;
-      }
-      SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
-      decide_ms += ms;
-    } else if (batches.size() > 1) {
-      // the next batch reuses d_pairs / d_items / h_items
-      SMB_CUDA_R(cudaStreamSynchronize(st));
-    }
+    SMB_CUDA_R(cudaEventRecord(ev_scored, st));
+    // ---- out stream: the header of this sub-batch (match total so far + its pairs' ranges)
+    SMB_CUDA_R(cudaStreamWaitEvent(so, ev_scored, 0));
+    SMB_CUDA_R(cudaMemcpyAsync(h->h_sub_counters.p + 4 * k, h->d_counters, 4 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, so));
+    SMB_CUDA_R(cudaMemcpyAsync(h->h_pair_out.p + sb.first, h->d_pair_out.p + sb.first,
+                               (sb.last - sb.first) * sizeof(PairOut), cudaMemcpyDeviceToHost, so));
+    SMB_CUDA_R(cudaEventRecord(ev_decided, so));
   }
 
-  // ---- results: header first (sizes), then exactly the matches that exist
-  SMB_CUDA_R(cudaMemcpyAsync(h->h_pair_out.p, h->d_pair_out.p, npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
-  SMB_CUDA_R(cudaMemcpyAsync(h->h_counters, h->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  // ---- results: as each sub-batch's header lands, copy exactly the matches it produced
+  size_t copied = 0;
+  for (size_t k = 0; k < subs.size(); ++k) {
+    SMB_CUDA_R(cudaEventSynchronize(h->ev_pool[4 * k + 1]));
+    const size_t upto = (size_t)h->h_sub_counters.p[4 * k];  // decide kernels reserve contiguously, in stream order
+    if (upto > out_cap || upto < copied) {
+      cudaStreamSynchronize(st);
+      cudaStreamSynchronize(so);
+      return give_back(fail(h, SMB_ECUDA, "internal error: %zu matches exceed capacity %zu", upto, out_cap));
+    }
+    if (upto > res->matches_cap) {
+      SMB_CUDA_R(cudaStreamSynchronize(so));  // earlier copies must have landed before the buffer moves
+      if (!ensure_matches(upto, copied)) {
+        cudaStreamSynchronize(st);
+        return give_back(fail(h, SMB_ENOMEM, "pinned result allocation of %zu matches failed", upto));
+      }
+    }
+    if (upto > copied)
+      SMB_CUDA_R(cudaMemcpyAsync(res->matches + copied, h->d_out.p + copied, (upto - copied) * sizeof(smb_match),
+                                 cudaMemcpyDeviceToHost, so));
+    copied = upto;
+  }
+  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[1], so));
+  SMB_CUDA_R(cudaStreamSynchronize(so));
   SMB_CUDA_R(cudaStreamSynchronize(st));
-  if (h->h_counters[3]) {  // the survivor log overflowed: this attempt's runner-up keys are incomplete
+  const unsigned long long* last = h->h_sub_counters.p + 4 * (subs.size() - 1);
+  if (last[3]) {  // the survivor log overflowed: this attempt's runner-up keys are incomplete
     *overflowed = true;
     return give_back(SMB_OK);
   }
-  const size_t total = (size_t)h->h_counters[0];
-  if (total > out_cap) return give_back(fail(h, SMB_ECUDA, "internal error: %zu matches exceed capacity %zu", total, out_cap));
-  if (total > res->matches_cap) {
-    if (res->matches) cudaFreeHost(res->matches);
-    res->matches = nullptr;
-    res->matches_cap = 0;
-    size_t want = std::max<size_t>(total, 4096);
-    SMB_CUDA_R(cudaMallocHost(&res->matches, want * sizeof(smb_match)));
-    res->matches_cap = want;
-  }
-  if (total) SMB_CUDA_R(cudaMemcpyAsync(res->matches, h->d_out.p, total * sizeof(smb_match), cudaMemcpyDeviceToHost, st));
-  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[1], st));
-  SMB_CUDA_R(cudaStreamSynchronize(st));
   std::memcpy(res->pair_out.data(), h->h_pair_out.p, npairs * sizeof(PairOut));
-  res->total = total;
+  res->total = copied;
   if (prof) {
-    float ms = 0.f;
+    float ms = 0.f, score_ms = 0.f;
     SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->timing.total_ms = ms;
+    for (size_t k = 0; k < subs.size(); ++k) {
+      if (!subs[k].items) continue;
+      SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev_pool[4 * k + 2], h->ev_pool[4 * k + 3]));
+      score_ms += ms;
+    }
     h->timing.score_ms = score_ms;
-    h->timing.decide_ms = decide_ms;
-    h->timing.candidates = h->h_counters[1];
+    h->timing.decide_ms = 0.f;  // overlapped with scoring on the second stream; see total_ms
+    h->timing.candidates = last[1];
   }
   h->timing.ops = ops;
-  (void)n_items_total;
-  (void)rc;
 #undef SMB_CUDA_R
   *out = res;
   return SMB_OK;

@@ -234,3 +234,16 @@ def test_full_size_ragged_properties():
         n1, n2 = sizes[prs[k][0]], sizes[prs[k][1]]
         assert (ab[:, 0] < n1).all() and (ab[:, 1] < n2).all()
     assert len(res[0]) > 50 and np.array_equal(res[7][:, 0], res[7][:, 1])
+
+
+def test_accumulator_budget_forces_sub_batches(oracle, monkeypatch):
+    """A small accumulator budget cuts one call into many sub-batches (score/decide per sub-batch, result
+    copies on the second stream); the concatenated results must be unchanged."""
+    ids = list(range(12))
+    imgs = [synth.make_image(i, 500 + 37 * i, track_step=24) for i in ids]
+    pairs = sequential_pairs(ids, 5)
+    monkeypatch.setenv("SMB_ACC_BUDGET", "3000")       # ~2 pairs per sub-batch
+    with SiftMatcher() as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+    assert total > 300
