@@ -105,6 +105,12 @@ int smb_put_image(smb_handle* h, uint32_t image_id, const uint8_t* desc, size_t 
 /* Batched form: all copies are queued, one wait at the end (the op uses it per stencil window). */
 int smb_put_images(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
                    size_t count, size_t d);
+/* Asynchronous form: the copies are queued on a dedicated upload stream and the call returns at once; the
+ * caller keeps the (pinned) buffers unchanged until smb_synchronize() or until a match call that names the
+ * images has returned.  smb_match_pairs waits (on the device) only for the uploads its own pairs depend on, so
+ * uploading the next images overlaps matching the previous ones. */
+int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
+                         size_t count, size_t d);
 /* Same, from device memory of this or a peer device (halo exchange over NVLink). */
 int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d);
 int smb_has_image(const smb_handle* h, uint32_t image_id);

@@ -572,6 +572,15 @@ score_dp4a_kernel(const uint8_t* __restrict__ pool, const WorkItem* __restrict__
   if (cand_counter && count) atomicAdd(cand_counter, count);
 }
 
+// Plan upload without the copy engine: the per-call plan (pair metas, work items) sits in pinned host memory,
+// which the device reads directly (UVA).  A cudaMemcpyAsync would queue behind whatever descriptor uploads
+// are already in the host->device copy engine's FIFO and stall the score kernel it feeds.
+__global__ void __launch_bounds__(256)
+fetch_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src_host, size_t n_words) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src_host[i];
+}
+
 // =====================================================================================
 // decide: FindBestMatchesOneWay tests + cross-check + ordered compaction, one CTA per pair
 // =====================================================================================

@@ -38,6 +38,7 @@ struct ImageEntry {
   uint32_t row0;   // first pool row
   uint32_t n;      // descriptor count
   uint32_t rows;   // reserved pool rows (multiple of kRowPad)
+  uint64_t up_seq; // 0 = resident; otherwise the upload ticket (smb_put_images_async) that fills it
 };
 
 struct Filter {
@@ -108,6 +109,11 @@ struct smb_handle {
   cudaStream_t stream = nullptr;      // uploads, accumulator clears, score kernels
   cudaStream_t stream_out = nullptr;  // decide kernels and result copies (overlap the next sub-batch's scoring)
   std::vector<cudaEvent_t> ev_pool;   // 4 per sub-batch: scored, decided, score begin/end
+  cudaStream_t stream_up = nullptr;   // asynchronous uploads (smb_put_images_async): copy engine under the score kernels
+  static constexpr int kUpRing = 64;
+  cudaEvent_t up_ev[kUpRing] = {};    // up_ev[t % kUpRing] fires when upload ticket t has landed
+  uint64_t up_issued = 0;             // last ticket handed out
+  uint64_t up_synced = 0;             // tickets <= this are known to have landed
   cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
 
   // descriptor pool
@@ -225,6 +231,8 @@ int apply_options(smb_handle* h, const smb_options* opts) {
 // kRowPad with zero rows (a zero descriptor scores 0 against everything and can never be a
 // candidate), so TMA boxes never need masking.
 // ------------------------------------------------------------------------------------------
+int drain_uploads(smb_handle* h);
+
 int encode_tmap(smb_handle* h) {
   h->tmap_valid = false;
   if (!h->pool_rows) return SMB_OK;
@@ -262,6 +270,7 @@ int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
   want = std::max<uint64_t>(want, (uint64_t)(64u << 20) / kDim);  // start at 64 MiB
   want = (want + kRowPad - 1) / kRowPad * kRowPad;
   if (want > 0xFFFFFF00ull) return fail(h, SMB_ENOMEM, "descriptor pool would exceed 2^32 rows");
+  if (int rc = drain_uploads(h)) return rc;  // pending uploads target the old allocation
   uint8_t* np = nullptr;
   SMB_CUDA(h, cudaMalloc(&np, want * kDim));
   if (h->pool) {
@@ -297,26 +306,39 @@ int alloc_rows(smb_handle* h, uint32_t rows, uint32_t* row0) {
   return fail(h, SMB_ENOMEM, "descriptor pool allocation of %u rows failed", rows);
 }
 
-int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_t d, cudaMemcpyKind kind) {
+// Everything queued on the upload stream has landed (needed before pool rows are recycled or the pool moves).
+int drain_uploads(smb_handle* h) {
+  if (h->up_synced != h->up_issued) {
+    SMB_CUDA(h, cudaStreamSynchronize(h->stream_up));
+    h->up_synced = h->up_issued;
+  }
+  return SMB_OK;
+}
+
+int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_t d, cudaMemcpyKind kind,
+                   cudaStream_t stream = nullptr, uint64_t up_seq = 0) {
+  if (!stream) stream = h->stream;
   if (d != (size_t)kDim) return fail(h, SMB_EINVAL, "descriptor dimension must be 128, got %zu", d);
   if (n && !src) return fail(h, SMB_EINVAL, "descriptor pointer is null");
   if (n > 0x7FFFFFFFu) return fail(h, SMB_EINVAL, "too many descriptors in one image: %zu", n);
   auto old = h->images.find(key);
   if (old != h->images.end()) {
-    // pairs already queued on the stream may still read the old rows
+    // pairs already queued on the stream may still read the old rows; a pending upload may still write them
     SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc = drain_uploads(h)) return rc;
     free_rows(h, old->second.row0, old->second.rows);
     h->images.erase(old);
   }
   ImageEntry e;
   e.n = (uint32_t)n;
   e.rows = (uint32_t)((n + kRowPad - 1) / kRowPad * kRowPad);
+  e.up_seq = up_seq;
   int rc = alloc_rows(h, e.rows, &e.row0);
   if (rc != SMB_OK) return rc;
   if (n) {
     uint8_t* dst = h->pool + (size_t)e.row0 * kDim;
-    SMB_CUDA(h, cudaMemcpyAsync(dst, src, n * kDim, kind, h->stream));
-    if (e.rows > n) SMB_CUDA(h, cudaMemsetAsync(dst + n * kDim, 0, (size_t)(e.rows - n) * kDim, h->stream));
+    SMB_CUDA(h, cudaMemcpyAsync(dst, src, n * kDim, kind, stream));
+    if (e.rows > n) SMB_CUDA(h, cudaMemsetAsync(dst + n * kDim, 0, (size_t)(e.rows - n) * kDim, stream));
   }
   h->images.emplace(key, e);
   return SMB_OK;
@@ -395,6 +417,8 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   SMB_CUDA_C(cudaSetDevice(cuda_device));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+  SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+  for (auto& e : h->up_ev) SMB_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev) SMB_CUDA_C(cudaEventCreate(&e));
   {
     void* fn = nullptr;
@@ -432,6 +456,7 @@ void smb_destroy(smb_handle* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream_out) cudaStreamSynchronize(h->stream_out);
+  if (h->stream_up) cudaStreamSynchronize(h->stream_up);
   for (smb_result* r : h->result_pool) {
     if (r->matches) cudaFreeHost(r->matches);
     delete r;
@@ -455,6 +480,9 @@ void smb_destroy(smb_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_out) cudaStreamDestroy(h->stream_out);
+  if (h->stream_up) cudaStreamDestroy(h->stream_up);
+  for (auto& e : h->up_ev)
+    if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -486,6 +514,22 @@ int smb_put_images(smb_handle* h, const uint32_t* image_ids, const uint8_t* cons
   return SMB_OK;
 }
 
+int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
+                         size_t count, size_t d) {
+  if (!h) return SMB_EINVAL;
+  if (count && (!image_ids || !descs || !ns)) return fail(h, SMB_EINVAL, "null array argument");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  if (h->up_issued - h->up_synced >= (uint64_t)smb_handle::kUpRing - 1)  // the event ring is about to wrap
+    if (int rc = drain_uploads(h)) return rc;
+  const uint64_t ticket = ++h->up_issued;
+  for (size_t k = 0; k < count; ++k) {
+    int rc = put_image_impl(h, image_ids[k], descs[k], ns[k], d, cudaMemcpyHostToDevice, h->stream_up, ticket);
+    if (rc != SMB_OK) return rc;
+  }
+  SMB_CUDA(h, cudaEventRecord(h->up_ev[ticket % smb_handle::kUpRing], h->stream_up));
+  return SMB_OK;
+}
+
 int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d) {
   if (!h) return SMB_EINVAL;
   SMB_CUDA(h, cudaSetDevice(h->device));
@@ -503,6 +547,7 @@ int smb_evict_image(smb_handle* h, uint32_t image_id) {
   if (it == h->images.end()) return fail(h, SMB_EINVAL, "image %u is not cached", image_id);
   SMB_CUDA(h, cudaSetDevice(h->device));
   SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc = drain_uploads(h)) return rc;
   free_rows(h, it->second.row0, it->second.rows);
   h->images.erase(it);
   return SMB_OK;
@@ -512,6 +557,7 @@ int smb_clear_images(smb_handle* h) {
   if (!h) return SMB_EINVAL;
   SMB_CUDA(h, cudaSetDevice(h->device));
   SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc = drain_uploads(h)) return rc;
   h->images.clear();
   h->free_list.clear();
   if (h->pool_rows) h->free_list.emplace(0u, h->pool_rows);
@@ -566,7 +612,7 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   const size_t target_pairs = npairs;
   const size_t sub_budget = h->acc_budget;
   size_t out_cap = 0, n_items_total = 0, max_acc = 0;
-  uint64_t ops = 0;
+  uint64_t ops = 0, wait_ticket = 0;  // newest asynchronous upload any of the pairs depends on
   {
     Sub cur{0, 0, 0, 0, 0, 0};
     for (size_t p = 0; p < npairs; ++p) {
@@ -576,6 +622,7 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
         return give_back(fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", p,
                               (unsigned long long)(i1 == h->images.end() ? keys[2 * p] : keys[2 * p + 1])));
       const ImageEntry &a = i1->second, &b = i2->second;
+      wait_ticket = std::max(wait_ticket, std::max(a.up_seq, b.up_seq));
       const size_t need = (size_t)a.n + b.n;
       if (p > cur.first && (cur.acc + need > sub_budget || p - cur.first >= target_pairs)) {
         cur.last = p;
@@ -666,10 +713,20 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   } while (0)
 
   if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
+  if (wait_ticket > h->up_synced)  // tickets complete in order on the upload stream: waiting for the newest is enough
+    SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[wait_ticket % smb_handle::kUpRing], 0));
   SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  SMB_CUDA_R(cudaMemcpyAsync(h->d_pairs.p, h->h_pairs.p, npairs * sizeof(PairMeta), cudaMemcpyHostToDevice, st));
-  if (n_items_total)
-    SMB_CUDA_R(cudaMemcpyAsync(h->d_items.p, h->h_items.p, n_items_total * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+  {  // plan upload by a kernel reading pinned host memory (not the copy engine, see fetch_words_kernel)
+    static_assert(sizeof(PairMeta) % 4 == 0 && sizeof(WorkItem) % 4 == 0, "plan structs are whole words");
+    const size_t wp = npairs * sizeof(PairMeta) / 4, wi = n_items_total * sizeof(WorkItem) / 4;
+    fetch_words_kernel<<<(unsigned)std::min<size_t>((wp + 255) / 256, 512), 256, 0, st>>>(
+        reinterpret_cast<uint32_t*>(h->d_pairs.p), reinterpret_cast<const uint32_t*>(h->h_pairs.p), wp);
+    if (wi)
+      fetch_words_kernel<<<(unsigned)std::min<size_t>((wi + 255) / 256, 512), 256, 0, st>>>(
+          reinterpret_cast<uint32_t*>(h->d_items.p), reinterpret_cast<const uint32_t*>(h->h_items.p), wi);
+    SMB_CUDA_R(cudaGetLastError());
+    h->timing.total_launches += wi ? 2 : 1;
+  }
   const SurvivorLog slog{use_log ? h->d_log.p : nullptr, h->d_counters + 2, (unsigned long long)h->log_cap};
   if (h->opts.engine == SMB_ENGINE_TCGEN05 && n_items_total && !h->tmap_valid)
     return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
@@ -865,7 +922,7 @@ int smb_synchronize(smb_handle* h) {
   if (!h) return SMB_EINVAL;
   SMB_CUDA(h, cudaSetDevice(h->device));
   SMB_CUDA(h, cudaStreamSynchronize(h->stream));
-  return SMB_OK;
+  return drain_uploads(h);
 }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_set_options.argtypes = [vp, ctypes.POINTER(smb_options)]
     L.smb_put_image.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_images.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
+    L.smb_put_images_async.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_image_device.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_has_image.argtypes = [vp, ctypes.c_uint32]
     L.smb_evict_image.argtypes = [vp, ctypes.c_uint32]
@@ -175,6 +176,18 @@ class SiftMatcher:
         ns = (ctypes.c_size_t * n)(*[d.shape[0] for d in ds])
         self._check(self._L.smb_put_images(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
                                            ctypes.cast(ns, ctypes.c_void_p), n, 128))
+
+    def put_images_async(self, image_ids: Sequence[int], descriptors: Sequence[np.ndarray]) -> None:
+        """Queue the uploads and return at once.  ``descriptors`` must stay alive and unchanged (pinned memory for
+        real overlap) until ``synchronize()`` or until a match call naming these images has returned."""
+        ds = [_desc(d) for d in descriptors]
+        n = len(ds)
+        self._keepalive = getattr(self, "_keepalive", [])[-256:] + ds
+        ids = np.asarray(list(image_ids), dtype=np.uint32)
+        ptrs = (ctypes.c_void_p * n)(*[d.ctypes.data for d in ds])
+        ns = (ctypes.c_size_t * n)(*[d.shape[0] for d in ds])
+        self._check(self._L.smb_put_images_async(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
+                                                 ctypes.cast(ns, ctypes.c_void_p), n, 128))
 
     def put_image_device(self, image_id: int, dev_ptr: int, n: int) -> None:
         self._check(self._L.smb_put_image_device(self._h, int(image_id), ctypes.c_void_p(dev_ptr), int(n), 128))

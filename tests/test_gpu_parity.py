@@ -247,3 +247,26 @@ def test_accumulator_budget_forces_sub_batches(oracle, monkeypatch):
         m.put_images(ids, imgs)
         total = _check_pairs(oracle, m, imgs, ids, pairs)
     assert total > 300
+
+
+def test_async_uploads_are_ordered_before_their_pairs(oracle):
+    """smb_put_images_async returns at once; a match call must still see every image it names (device-side
+    wait on the upload ticket), also across re-puts, evictions and pool growth."""
+    import torch
+    ids = list(range(8))
+    imgs = [torch.from_numpy(synth.make_image(i, 3000 + 100 * i, track_step=96)).pin_memory().numpy() for i in ids]
+    with SiftMatcher() as m:
+        for k in range(0, 8, 2):
+            m.put_images_async(ids[k:k + 2], imgs[k:k + 2])
+        _check_pairs(oracle, m, imgs, ids, sequential_pairs(ids, 4))
+        # replace two images while nothing is synchronised, then match again
+        imgs[3] = torch.from_numpy(synth.make_image(33, 2500, track_step=96)).pin_memory().numpy()
+        imgs[4] = torch.from_numpy(synth.make_image(44, 3500, track_step=96)).pin_memory().numpy()
+        m.put_images_async([3, 4], [imgs[3], imgs[4]])
+        _check_pairs(oracle, m, imgs, ids, np.array([[2, 3], [3, 4], [4, 5]], dtype=np.uint32))
+        m.evict_image(0)
+        big = [torch.from_numpy(synth.make_image(100 + i, 8192, track_step=512)).pin_memory().numpy() for i in range(70)]
+        m.put_images_async(range(100, 170), big)        # > 64 MiB: the pool grows underneath pending uploads
+        _check_pairs(oracle, m, [big[0], big[1], big[69], imgs[5]], [100, 101, 169, 5],
+                     np.array([[100, 101], [169, 5]], dtype=np.uint32))
+        m.synchronize()
