@@ -229,8 +229,7 @@ def run_ours(args):
             return torch.as_tensor(_DevView(ptr, n * 128), device=dev)
         sharding.exchange_halo(sp, view, lambda row: halo_buf[row])
         torch.cuda.current_stream().synchronize()
-        for row in halo_ids:
-            m.put_image_device(row, halo_buf[row].data_ptr(), N_DESC)
+        m.put_images_device(halo_ids, [halo_buf[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids))
 
     def barrier():
         if world > 1:

@@ -113,6 +113,8 @@ int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t
                          size_t count, size_t d);
 /* Same, from device memory of this or a peer device (halo exchange over NVLink). */
 int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d);
+int smb_put_images_device(smb_handle* h, const uint32_t* image_ids, const void* const* dev_descs, const size_t* ns,
+                          size_t count, size_t d);
 int smb_has_image(const smb_handle* h, uint32_t image_id);
 int smb_evict_image(smb_handle* h, uint32_t image_id);
 int smb_clear_images(smb_handle* h);

@@ -539,6 +539,19 @@ int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc,
   return SMB_OK;
 }
 
+int smb_put_images_device(smb_handle* h, const uint32_t* image_ids, const void* const* dev_descs, const size_t* ns,
+                          size_t count, size_t d) {
+  if (!h) return SMB_EINVAL;
+  if (count && (!image_ids || !dev_descs || !ns)) return fail(h, SMB_EINVAL, "null array argument");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  for (size_t k = 0; k < count; ++k) {
+    int rc = put_image_impl(h, image_ids[k], dev_descs[k], ns[k], d, cudaMemcpyDefault);
+    if (rc != SMB_OK) return rc;
+  }
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
 int smb_has_image(const smb_handle* h, uint32_t image_id) { return h && h->images.count(image_id) ? 1 : 0; }
 
 int smb_evict_image(smb_handle* h, uint32_t image_id) {

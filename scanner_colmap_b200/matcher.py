@@ -74,6 +74,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_put_images.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_images_async.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_image_device.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_size_t]
+    L.smb_put_images_device.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_has_image.argtypes = [vp, ctypes.c_uint32]
     L.smb_evict_image.argtypes = [vp, ctypes.c_uint32]
     L.smb_clear_images.argtypes = [vp]
@@ -191,6 +192,14 @@ class SiftMatcher:
 
     def put_image_device(self, image_id: int, dev_ptr: int, n: int) -> None:
         self._check(self._L.smb_put_image_device(self._h, int(image_id), ctypes.c_void_p(dev_ptr), int(n), 128))
+
+    def put_images_device(self, image_ids: Sequence[int], dev_ptrs: Sequence[int], ns: Sequence[int]) -> None:
+        n = len(dev_ptrs)
+        ids = np.asarray(list(image_ids), dtype=np.uint32)
+        ptrs = (ctypes.c_void_p * n)(*[int(p) for p in dev_ptrs])
+        cnt = (ctypes.c_size_t * n)(*[int(x) for x in ns])
+        self._check(self._L.smb_put_images_device(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
+                                                  ctypes.cast(cnt, ctypes.c_void_p), n, 128))
 
     def has_image(self, image_id: int) -> bool:
         return bool(self._L.smb_has_image(self._h, int(image_id)))
