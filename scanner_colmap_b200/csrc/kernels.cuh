@@ -391,32 +391,59 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
+    // The tensor pipe queues only an instruction or two ahead of the issuing thread (measured: ~50 extra
+    // instructions between groups of four MMAs cost 28 % of the MMA rate), so the loop is software-pipelined:
+    // the barrier waits for the NEXT tile (already-complete try_waits still cost ~90 clk each) are done right
+    // after the current tile's MMAs have been issued, while those execute.
+    if (lane == 0 && blockIdx.x < n_items) {
       constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kMTile, kTileCols);
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, ts = 0, tph = 0;
-      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const uint32_t n_btiles = items[it].n_btiles, m_tiles = items[it].m_tiles;
-        ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
-        const uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
-        for (uint32_t t = 0; t < n_btiles; ++t) {
-          ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
-          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
-          for (uint32_t mh = 0; mh < m_tiles; ++mh) {
-            ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
-            ptx::tcgen05_fence_after();
-            const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
-            const uint32_t d = tmem_base + ts * kTileCols;
+      uint32_t it = blockIdx.x, t = 0, mh = 0;
+      uint32_t n_btiles = items[it].n_btiles, m_tiles = items[it].m_tiles;
+      uint32_t nxt_nb = 0, nxt_mt = 0;  // next item's shape, fetched a whole item ahead of its use
+      if (it + gridDim.x < n_items) {
+        nxt_nb = items[it + gridDim.x].n_btiles;
+        nxt_mt = items[it + gridDim.x].m_tiles;
+      }
+      ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
+      ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
+      ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
+      ptx::tcgen05_fence_after();
+      uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
+      uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
+      for (;;) {
+        const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
+        const uint32_t d = tmem_base + ts * kTileCols;
 #pragma unroll
-            for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
-              ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
-            ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
-            if (++ts == 2) { ts = 0; tph ^= 1; }
-          }
+        for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
+          ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+        ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
+        if (++ts == 2) { ts = 0; tph ^= 1; }
+        // ---- everything below overlaps the execution of the MMAs just issued
+        if (++mh == m_tiles) {
+          mh = 0;
           ptx::umma_commit(ptx::smem_u32(&sh->b_empty[bs]));
           if (++bs == kStages) { bs = 0; bph ^= 1; }
+          if (++t == n_btiles) {
+            t = 0;
+            ptx::umma_commit(ptx::smem_u32(&sh->a_empty[as]));
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+            it += gridDim.x;
+            if (it >= n_items) break;
+            n_btiles = nxt_nb;
+            m_tiles = nxt_mt;
+            if (it + gridDim.x < n_items) {
+              nxt_nb = items[it + gridDim.x].n_btiles;
+              nxt_mt = items[it + gridDim.x].m_tiles;
+            }
+            ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
+            adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
+          }
+          ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
+          bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
         }
-        ptx::umma_commit(ptx::smem_u32(&sh->a_empty[as]));
-        if (++as == kAStages) { as = 0; aph ^= 1; }
+        ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
+        ptx::tcgen05_fence_after();
       }
     }
   } else if (warp >= 4) {

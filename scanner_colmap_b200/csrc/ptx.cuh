@@ -76,9 +76,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t pa
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+#ifdef SMB_MBAR_BUSY_POLL
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (SMB_MBAR_SPIN_LIMIT << 4)) __trap();
+  }
+#else
   while (!mbar_try_wait_hint(bar, parity, 4000u)) {
     if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
   }
+#endif
 }
 
 // ---------------------------------------------------------------- TMA

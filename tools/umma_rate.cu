@@ -27,11 +27,12 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
                  : "memory");
 }
 
-__device__ int g_fill_mode = 0;  // 0: constant bytes, 1: pseudo-random bytes, 2: zeros
+__device__ int g_fill_mode = 0;
+__device__ int g_commit_every = 0;  // 0: one commit at the end; n: commit to a scratch barrier after every n-th group of k_steps MMAs  // 0: constant bytes, 1: pseudo-random bytes, 2: zeros
 template <int KIND>
 __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t idesc, int iters, int n_cols, int k_steps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // zero the operand tiles so fp kinds see no NaN patterns
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t idesc, int iters,
         g_fill_mode == 0 ? 0x01010101u : g_fill_mode == 2 ? 0u : ((x * 2654435761u) ^ (x >> 3) * 40503u) & (KIND == I8 ? 0xFFFFFFFFu : 0x3F3F3F3Fu);
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
+    mbar_init(smem_u32(&bar2), 1u << 20);  // never completes: a pure commit target
     fence_barrier_init();
   }
   if (threadIdx.x < 32) {
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t idesc, int iters,
     for (int i = 0; i < iters; ++i) {
       const uint32_t d = tb + (n_cols <= 160 ? (i % 3) : (i & 1)) * n_cols;
       for (int k = 0; k < k_steps; ++k) mma<KIND>(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+      if (g_commit_every && (i % g_commit_every) == g_commit_every - 1) umma_commit(smem_u32(&bar2));
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -107,10 +110,12 @@ void run(const char* name, int afmt, int bfmt, int m, int n, int k_steps, int gr
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  for (int mode : {1})
-  for (int grid : {1, sms}) {
+  for (int ce : {0, 1, 2})
+  for (int grid : {sms}) {
+    int mode = 1;
     cudaMemcpyToSymbol(g_fill_mode, &mode, sizeof(int));
-    printf("--- fill mode %d (0 const, 1 random, 2 zero)\n", mode);
+    cudaMemcpyToSymbol(g_commit_every, &ce, sizeof(int));
+    printf("--- commit every %d group(s) of 4 MMAs (0 = only at the end)\n", ce);
     run<I8>("i8  u8 x u8", 0, 0, 128, 256, 4, grid);
     run<I8>("i8  s8 x s8", 1, 1, 128, 256, 4, grid);
     run<I8>("i8  u8 x u8 N=128", 0, 0, 128, 128, 4, grid);
