@@ -470,22 +470,18 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
           ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
           ptx::tmem_wait_ld();
-          const int mc0 = max_tree32(v0), mc1 = max_tree32(v1), mc2 = max_tree32(v2), mc3 = max_tree32(v3);
-          // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp
+          // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp at once -- the
+          // hand-off latency (commit -> wake -> read -> arrive -> wake, ~350 clk + this read), not the
+          // arithmetic, is what the two TMEM buffers have to cover
           ptx::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
-          // Which of this thread's four runs hold a survivor (rare).  One ballot for the whole warp; the few
-          // lanes concerned are then served one after the other with warp-uniform control flow, so the common
-          // case (one lane, one run) costs a ballot, a shuffle and nine vector stores.  Single producer (this
-          // warp) / single consumer (its insert warp) ring: no atomics; the consumer's tail is re-read only
-          // when the cached copy says the ring is full.  Pool padding rows are all-zero descriptors
-          // (score 0 < min_score), so no bounds test is needed.
-          const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
-                              (mc3 >= min_score ? 8u : 0u);
-          uint32_t lanes = __ballot_sync(0xffffffffu, hm != 0);
+          const int mc0 = max_tree32(v0), mc1 = max_tree32(v1), mc2 = max_tree32(v2), mc3 = max_tree32(v3);
+          uint32_t lanes = __ballot_sync(0xffffffffu, __vimax3_s32(mc0, mc1, max(mc2, mc3)) >= min_score);
           if (lanes && !(dbg & 4)) {
+            const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
+                                (mc3 >= min_score ? 8u : 0u);
             const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
             do {
               const int src = __ffs(lanes) - 1;
