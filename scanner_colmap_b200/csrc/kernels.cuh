@@ -101,16 +101,19 @@ constexpr int kAStages = 2;                    // A-strip ring (next item's stri
 constexpr int kMTile = 128;                    // UMMA M
 constexpr int kABytes = 2 * kMTile * kDim;     // 32 KiB (two 128-row boxes)
 constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
-constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter (one per 128-column half)
-constexpr int kEpiCols = kTileCols / 2;        // 128 accumulator columns per warp and tile
+#ifndef SMB_EPI_WARPS
+#define SMB_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = SMB_EPI_WARPS;       // 2 or 4 per TMEM lane quarter, each a column slice of the tile
+constexpr int kEpiCols = kTileCols / (kEpiWarps / 4);  // accumulator columns per warp and tile
 constexpr int kInsertWarps = 2;                // warps 2 and 3
-constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4-11 epilogue
+constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4.. epilogue
 constexpr int kScoreThreads = 32 * kScoreWarps;
 constexpr int kRunCols = 32;                   // accumulator columns per thread per tcgen05.ld
-constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 4, all in flight at once
-constexpr int kMailSlots = 16;                 // per epilogue warp: ring of survivor runs
+constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 2 or 4, all in flight at once
+constexpr int kMailSlots = 128 / kEpiWarps;    // per epilogue warp: ring of survivor runs
 constexpr int kInsertBatch = 4;                // runs an insert warp handles per L2 round trip
-static_assert(kRunsPerWarp == 4, "epilogue code is written for four 32-column runs per warp");
+static_assert(kRunsPerWarp == 4 || kRunsPerWarp == 2, "epilogue code is written for two or four 32-column runs per warp");
 
 // A 32-column run of one accumulator row that holds at least one score >= min_score, copied out of the
 // epilogue thread's registers: the exact scores themselves, no recomputation.
@@ -464,11 +467,13 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + col0;
-          uint32_t v0[32], v1[32], v2[32], v3[32];  // all four runs in flight; ptxas tracks each load's registers
+          uint32_t v0[32], v1[32], v2[32], v3[32];  // all runs in flight; ptxas tracks each load's registers
           ptx::tmem_ld_32x32b_x32(taddr, v0);
           ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
-          ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
-          ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
+          if constexpr (kRunsPerWarp == 4) {
+            ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
+            ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
+          }
           ptx::tmem_wait_ld();
           // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp at once -- the
           // hand-off latency (commit -> wake -> read -> arrive -> wake, ~350 clk + this read), not the
@@ -477,7 +482,12 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
-          const int mc0 = max_tree32(v0), mc1 = max_tree32(v1), mc2 = max_tree32(v2), mc3 = max_tree32(v3);
+          const int mc0 = max_tree32(v0), mc1 = max_tree32(v1);
+          int mc2 = -1, mc3 = -1;  // below every score and every min_score (>= 0)
+          if constexpr (kRunsPerWarp == 4) {
+            mc2 = max_tree32(v2);
+            mc3 = max_tree32(v3);
+          }
           uint32_t lanes = __ballot_sync(0xffffffffu, __vimax3_s32(mc0, mc1, max(mc2, mc3)) >= min_score);
           if (lanes && !(dbg & 4)) {
             const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
@@ -501,8 +511,10 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
                 uint32_t pos = mail_head;
                 if (m & 1u) store_run(sh, e, pos++, v0, rslot, cslot);
                 if (m & 2u) store_run(sh, e, pos++, v1, rslot, cslot + kRunCols);
-                if (m & 4u) store_run(sh, e, pos++, v2, rslot, cslot + 2 * kRunCols);
-                if (m & 8u) store_run(sh, e, pos++, v3, rslot, cslot + 3 * kRunCols);
+                if constexpr (kRunsPerWarp == 4) {
+                  if (m & 4u) store_run(sh, e, pos++, v2, rslot, cslot + 2 * kRunCols);
+                  if (m & 8u) store_run(sh, e, pos++, v3, rslot, cslot + 3 * kRunCols);
+                }
               }
               mail_head += need;
             } while (lanes);
