@@ -92,27 +92,34 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 //                 keys with fire-and-forget RED.MAX and are appended to a survivor log, from which
 //                 runner_up_kernel settles the second-best keys afterwards.
 //
-// (A cta_group::2 variant -- CTA pairs sharing each B tile -- was built and measured slower on this
-// workload: with K = 128 the tile pipeline is bound by the accumulator hand-off latency, which the
-// cross-CTA barriers lengthen; see DESIGN.md "Kernel history".)
+// Where the time goes (build with -DSMB_TRACE, run tools/trace_case.py): the kernel is bound by the epilogue
+// warps' serial per-tile chain -- barrier wait (~150 clk even when complete: every shared-memory access
+// queues behind the MMA operand reads), tcgen05.ld (~165), then the max trees of the two warps that share an
+// SMSP's ALU pipe (~300) -- not by the tensor pipe (512 clk per tile), and each survivor run a warp posts
+// costs it another ~400 clk of shared-memory stores.  Variants built and measured slower: cta_group::2 CTA
+// pairs, 16 epilogue warps, two MMA issuer threads with setmaxnreg warpgroups, N = 160 x 3 / N = 128 x 4
+// TMEM buffers (DESIGN.md "Kernel history").
 // =====================================================================================
 constexpr int kStages = 4;                     // B-tile ring
 constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
 constexpr int kMTile = 128;                    // UMMA M
 constexpr int kABytes = 2 * kMTile * kDim;     // 32 KiB (two 128-row boxes)
 constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
+#ifndef SMB_IDLE_NS
+#define SMB_IDLE_NS 200
+#endif
 #ifndef SMB_EPI_WARPS
 #define SMB_EPI_WARPS 8
 #endif
 constexpr int kEpiWarps = SMB_EPI_WARPS;       // 2 or 4 per TMEM lane quarter, each a column slice of the tile
 constexpr int kEpiCols = kTileCols / (kEpiWarps / 4);  // accumulator columns per warp and tile
 constexpr int kInsertWarps = 2;                // warps 2 and 3
+constexpr int kInsertWarp0 = 2;
 constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4.. epilogue
 constexpr int kScoreThreads = 32 * kScoreWarps;
 constexpr int kRunCols = 32;                   // accumulator columns per thread per tcgen05.ld
 constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 2 or 4, all in flight at once
 constexpr int kMailSlots = 128 / kEpiWarps;    // per epilogue warp: ring of survivor runs
-constexpr int kInsertBatch = 4;                // runs an insert warp handles per L2 round trip
 static_assert(kRunsPerWarp == 4 || kRunsPerWarp == 2, "epilogue code is written for two or four 32-column runs per warp");
 
 // A 32-column run of one accumulator row that holds at least one score >= min_score, copied out of the
@@ -134,7 +141,6 @@ struct ScoreShared {
   uint32_t epi_done;              // epilogue warps that have finished
   uint32_t tmem_base;
   uint32_t pad_[2];
-  uint4 jobs[kInsertWarps][32];   // per insert warp: compacted (row slot, column slot, score) insertions
   HitRun mail[kEpiWarps][kMailSlots];
 };
 constexpr int kScoreSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kStages * kBBytes + (int)sizeof(ScoreShared);
@@ -154,10 +160,25 @@ __device__ __forceinline__ int max_tree32(const uint32_t (&v)[32]) {
   return max(__vimax3_s32(b0, b1, b2), b3);
 }
 
+#ifdef SMB_TRACE
+__device__ uint32_t g_tr[3][64][4];  // [MMA, -, epilogue warp 0][tile index][event] clock stamps of CTA 0
+__device__ __forceinline__ uint32_t tr_clock() {
+  uint32_t c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c)::"memory");
+  return c;
+}
+#endif
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
+  return v;
+}
+// Acquire load (CTA scope) of a shared-memory word: orders the loads that follow it without waiting for this
+// thread's outstanding global stores/atomics, which a fence would (measured: ~2500 clk per insert pass).
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -187,9 +208,11 @@ struct SurvivorLog {
   unsigned long long capacity;
 };
 
-// Insert warp r serves the mailboxes of epilogue warps r, r + 2, r + 4, r + 6.  Lane l looks at column
-// (run + l) of every run: a score >= min_score is a survivor of its row and its column.  Up to kInsertBatch
-// runs are taken per pass and their survivors are compacted onto consecutive lanes.
+// Insert warp r serves the mailboxes of epilogue warps r, r + kInsertWarps, ...  Lane l looks at column (run + l)
+// of every posted run: a score >= min_score is a survivor of its row and its column.  The loop is kept short on
+// purpose (one run per iteration, no batching): with the survivor log nothing here waits for global memory, and
+// an earlier batched/compacting version spent ~1400 clk per pass on its own instruction stream and throttled
+// the epilogue through mailbox back-pressure (measured with -DSMB_TRACE).
 __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict__ acc, SurvivorLog slog, int min_score,
                                             uint32_t r, uint32_t lane, unsigned long long* cand_counter, uint32_t dbg) {
   constexpr int kBoxes = kEpiWarps / kInsertWarps;
@@ -199,67 +222,35 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
   uint32_t count = 0;
   unsigned long long chunk_pos = 0;  // next free entry of this warp's current log chunk
   uint32_t chunk_left = 0;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#ifdef SMB_TRACE
+  uint32_t tr_busy = 0, tr_passes = 0, tr_runs = 0, tr_idle_polls = 0;
+  const uint32_t tr_start = tr_clock();
+#endif
   for (;;) {
-    uint32_t row_slot[kInsertBatch], col_slot[kInsertBatch], sc[kInsertBatch];
+#ifdef SMB_TRACE
+    const uint32_t tr0 = tr_clock();
+#endif
     uint32_t got = 0;
-#pragma unroll
-    for (int b = 0; b < kInsertBatch; ++b) {
-      row_slot[b] = col_slot[b] = 0;
-      sc[b] = 0;
-    }
 #pragma unroll
     for (int k = 0; k < kBoxes; ++k) {
       const uint32_t e = r + k * kInsertWarps;
-      const uint32_t head = ld_volatile_shared(&sh->mail_head[e]);
-      uint32_t took = 0;
-#pragma unroll
-      for (int b = 0; b < kInsertBatch; ++b) {
-        if (got == (uint32_t)b && tail[k] != head) {  // warp-uniform
-          if (took == 0) fence_cta();
-          const uint32_t src = ptx::smem_u32(&sh->mail[e][tail[k] % kMailSlots]);
-          uint32_t rs, cs;
-          asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rs), "=r"(cs) : "r"(src) : "memory");
-          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(sc[b]) : "r"(src + 16 + lane * 4) : "memory");
-          row_slot[b] = rs;
-          col_slot[b] = cs + lane;
-          ++tail[k];
-          ++took;
-          ++got;
-        }
-      }
-      if (took) {
-        __syncwarp();  // every lane has read the entries before they may be reused
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_tail[e]) = tail[k];
-      }
-    }
-    if (got) {
-      // compact the survivors of the batch: survivor (run b, lane) becomes job pre[b] + (its rank in run b);
-      // lane j then performs job j, so every insertion of the batch is in flight in the same instructions
-      uint32_t bal[kInsertBatch], pre[kInsertBatch + 1];
-      pre[0] = 0;
-#pragma unroll
-      for (int b = 0; b < kInsertBatch; ++b) {
-        bal[b] = __ballot_sync(0xffffffffu, (int)sc[b] >= min_score);
-        pre[b + 1] = pre[b] + __popc(bal[b]);
-      }
-      const uint32_t total = (dbg & 8) ? 0u : pre[kInsertBatch];
-      for (uint32_t base = 0; base < total; base += 32) {
-#pragma unroll
-        for (int b = 0; b < kInsertBatch; ++b) {
-          const uint32_t job = pre[b] + __popc(bal[b] & ((1u << lane) - 1));
-          if ((int)sc[b] >= min_score && job - base < 32u)
-            st_shared_v4(ptx::smem_u32(&sh->jobs[r][job - base]), row_slot[b], col_slot[b], sc[b], 0u);
-        }
-        __syncwarp();
-        const uint32_t njobs = total - base < 32u ? total - base : 32u;
-        uint32_t jr = 0, jc = 0, js = 0, jp = 0;
-        if (lane < njobs)
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(jr), "=r"(jc), "=r"(js), "=r"(jp)
-                       : "r"(ptx::smem_u32(&sh->jobs[r][lane]))
-                       : "memory");
+      const uint32_t head = ld_acquire_shared(&sh->mail_head[e]);
+      if (tail[k] == head) continue;  // warp-uniform
+      do {
+        const uint32_t src = ptx::smem_u32(&sh->mail[e][tail[k] % kMailSlots]);
+        uint32_t rs, cs, sc;
+        asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rs), "=r"(cs) : "r"(src) : "memory");
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(sc) : "r"(src + 16 + lane * 4) : "memory");
+        ++tail[k];
+        ++got;
+        const bool surv = (int)sc >= min_score;
+        const uint32_t bal = __ballot_sync(0xffffffffu, surv);
+        const uint32_t n = __popc(bal);
+        if (n == 0 || (dbg & 8)) continue;  // warp-uniform (cannot happen for n unless the ring is misused)
+        cs += lane;
         if (slog.entries) {
-          if (chunk_left < njobs) {  // warp-uniform: retire the chunk (zero its tail) and reserve a new one
+          if (chunk_left < n) {  // retire the chunk (zero its tail) and reserve a new one
             for (uint32_t x = lane; x < chunk_left; x += 32)
               if (chunk_pos + x < slog.capacity) slog.entries[chunk_pos + x] = make_uint4(0, 0, 0, 0);
             unsigned long long p = 0;
@@ -267,20 +258,32 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
             chunk_pos = __shfl_sync(0xffffffffu, p, 0);
             chunk_left = kLogChunk;
           }
-          if (lane < njobs) {
-            atomicMax(&acc[jr].k1, make_key(js, jc));  // results unused: RED, nothing to wait for
-            atomicMax(&acc[jc].k1, make_key(js, jr));
-            if (chunk_pos + lane < slog.capacity) slog.entries[chunk_pos + lane] = make_uint4(jr, jc, js, 0u);
+          if (surv) {
+            atomicMax(&acc[rs].k1, make_key(sc, cs));  // results unused: nothing to wait for
+            atomicMax(&acc[cs].k1, make_key(sc, rs));
+            const unsigned long long pos = chunk_pos + __popc(bal & lt_mask);
+            if (pos < slog.capacity) slog.entries[pos] = make_uint4(rs, cs, sc, 0u);
           }
-          chunk_pos += njobs;
-          chunk_left -= njobs;
-        } else if (lane < njobs) {
-          top2_insert2(acc, jr, jc, js);
+          chunk_pos += n;
+          chunk_left -= n;
+        } else if (surv) {
+          top2_insert2(acc, rs, cs, sc);
         }
-        count += lane < njobs;
-        __syncwarp();
-      }
+        count += surv;
+      } while (tail[k] != head);
+      __syncwarp();  // every lane has read the entries before they may be reused
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_tail[e]) = tail[k];
+    }
+    if (got) {
+#ifdef SMB_TRACE
+      tr_busy += tr_clock() - tr0;
+      ++tr_passes;
+      tr_runs += got;
+#endif
     } else {
+#ifdef SMB_TRACE
+      ++tr_idle_polls;
+#endif
       if (ld_volatile_shared(&sh->epi_done) == (uint32_t)kEpiWarps) {
         fence_cta();
         bool drained = true;
@@ -289,7 +292,7 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
           if (ld_volatile_shared(&sh->mail_head[r + k * kInsertWarps]) != tail[k]) drained = false;
         if (drained) break;  // epi_done is bumped only after that warp's last post is visible
       } else {
-        __nanosleep(200);
+        __nanosleep(SMB_IDLE_NS);
       }
     }
   }
@@ -297,6 +300,11 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
     for (uint32_t x = lane; x < chunk_left; x += 32)
       if (chunk_pos + x < slog.capacity) slog.entries[chunk_pos + x] = make_uint4(0, 0, 0, 0);
   if (cand_counter && count) atomicAdd(cand_counter, (unsigned long long)count);
+#ifdef SMB_TRACE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("INS %u total %u busy %u passes %u runs %u idle polls %u | clk per pass %.1f runs per pass %.2f\n", r, tr_clock() - tr_start,
+           tr_busy, tr_passes, tr_runs, tr_idle_polls, (float)tr_busy / (tr_passes ? tr_passes : 1), (float)tr_runs / (tr_passes ? tr_passes : 1));
+#endif
 }
 
 // Second stage of the logged insertion: every survivor that is not the final best of its row (column)
@@ -414,7 +422,13 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
       ptx::tcgen05_fence_after();
       uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
       uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
+#ifdef SMB_TRACE
+      uint32_t tr_tiles = 0;
+#endif
       for (;;) {
+#ifdef SMB_TRACE
+        const uint32_t tr0 = tr_clock();
+#endif
         const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
         const uint32_t d = tmem_base + ts * kTileCols;
 #pragma unroll
@@ -422,6 +436,13 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
         ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
         if (++ts == 2) { ts = 0; tph ^= 1; }
+#ifdef SMB_TRACE
+        if (blockIdx.x == 0 && tr_tiles < 64) {
+          g_tr[0][tr_tiles][0] = tr0;         // first MMA of the tile handed to the tensor pipe
+          g_tr[0][tr_tiles][1] = tr_clock();  // commit accepted
+        }
+        ++tr_tiles;
+#endif
         // ---- everything below overlaps the execution of the MMAs just issued
         if (++mh == m_tiles) {
           mh = 0;
@@ -456,6 +477,10 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     const uint32_t col0 = (e >> 2) * kEpiCols;  // which 128 of the tile's 256 columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
     uint32_t ts = 0, tph = 0, mail_head = 0, mail_tail_seen = 0;
+#ifdef SMB_TRACE
+    uint32_t tr_wait = 0, tr_ld = 0, tr_rel = 0, tr_tree = 0, tr_post = 0, tr_tiles = 0, tr_posts = 0, tr_bp = 0, tr_bpn = 0, tr_store = 0, tr_pub = 0, tr_postonly = 0;
+    const uint32_t tr_start = tr_clock();
+#endif
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairMeta pm = pairs[w.pair];
@@ -464,8 +489,16 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
       const uint32_t col_slot0 = pm.acc_off + pm.n1 + col0;
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
+#ifdef SMB_TRACE
+          const uint32_t tr0 = tr_clock();
+#endif
           ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
+#ifdef SMB_TRACE
+          const uint32_t tr1 = tr_clock();
+          tr_wait += tr1 - tr0;
+          ++tr_tiles;
+#endif
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + col0;
           uint32_t v0[32], v1[32], v2[32], v3[32];  // all runs in flight; ptxas tracks each load's registers
           ptx::tmem_ld_32x32b_x32(taddr, v0);
@@ -475,13 +508,21 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
             ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
           }
           ptx::tmem_wait_ld();
-          // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp at once -- the
-          // hand-off latency (commit -> wake -> read -> arrive -> wake, ~350 clk + this read), not the
-          // arithmetic, is what the two TMEM buffers have to cover
+#ifdef SMB_TRACE
+          const uint32_t tr2 = tr_clock();
+          tr_ld += tr2 - tr1;
+#endif
+          // every accumulator value of the tile is in registers: hand the TMEM buffer back to the MMA warp at
+          // once -- the hand-off latency (commit -> wake -> read -> arrive -> wake), not the arithmetic, is what
+          // the two TMEM buffers have to cover
           ptx::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
+#ifdef SMB_TRACE
+          const uint32_t tr3 = tr_clock();
+          tr_rel += tr3 - tr2;
+#endif
           const int mc0 = max_tree32(v0), mc1 = max_tree32(v1);
           int mc2 = -1, mc3 = -1;  // below every score and every min_score (>= 0)
           if constexpr (kRunsPerWarp == 4) {
@@ -489,6 +530,11 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
             mc3 = max_tree32(v3);
           }
           uint32_t lanes = __ballot_sync(0xffffffffu, __vimax3_s32(mc0, mc1, max(mc2, mc3)) >= min_score);
+#ifdef SMB_TRACE
+          const uint32_t tr4 = tr_clock();
+          tr_tree += tr4 - tr3;
+          if (lanes && !(dbg & 4)) ++tr_posts;
+#endif
           if (lanes && !(dbg & 4)) {
             const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
                                 (mc3 >= min_score ? 8u : 0u);
@@ -502,11 +548,21 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
                 __syncwarp();  // publish what has been written so far, or the consumer could never make room
                 if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = mail_head;
                 uint32_t spins = 0;
+#ifdef SMB_TRACE
+                const uint32_t trb = tr_clock();
+#endif
                 do {
                   mail_tail_seen = ld_volatile_shared(&sh->mail_tail[e]);
                   if (++spins > (1u << 28)) __trap();
                 } while (mail_head + need - mail_tail_seen > (uint32_t)kMailSlots);
+#ifdef SMB_TRACE
+                tr_bp += tr_clock() - trb;
+                ++tr_bpn;
+#endif
               }
+#ifdef SMB_TRACE
+              const uint32_t trs0 = tr_clock();
+#endif
               if (lane == (uint32_t)src) {
                 uint32_t pos = mail_head;
                 if (m & 1u) store_run(sh, e, pos++, v0, rslot, cslot);
@@ -517,17 +573,43 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
                 }
               }
               mail_head += need;
+#ifdef SMB_TRACE
+              __syncwarp();
+              tr_store += tr_clock() - trs0;
+#endif
             } while (lanes);
+#ifdef SMB_TRACE
+            const uint32_t trs1 = tr_clock();
+#endif
             // No MEMBAR (it would wait ~300+ clk for the vector stores above, on the tile pipeline's critical
             // warp): __syncwarp orders the lanes, so lane 0's store of the new head is issued after every
             // lane's payload stores, and one warp's shared-memory stores are performed in issue order by the
             // SM's single shared-memory pipe.  The consumer pairs this with a fence after reading the head.
             __syncwarp();
             if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_head[e]) = mail_head;
+#ifdef SMB_TRACE
+            tr_pub += tr_clock() - trs1;
+            tr_postonly += tr_clock() - tr4;
+#endif
           }
+#ifdef SMB_TRACE
+          tr_post += tr_clock() - tr4;
+          if (blockIdx.x == 0 && e == 0 && lane == 0 && tr_tiles - 1 < 64) {
+            g_tr[2][tr_tiles - 1][0] = tr0;
+            g_tr[2][tr_tiles - 1][1] = tr1;
+            g_tr[2][tr_tiles - 1][2] = tr3;
+            g_tr[2][tr_tiles - 1][3] = tr_clock();
+          }
+#endif
         }
       }
     }
+#ifdef SMB_TRACE
+    if (blockIdx.x == 0 && lane == 0)
+      printf("EPI %2u tiles %u posts %u total %u | per tile: total %.1f wait %.1f ld %.1f rel %.1f tree %.1f post %.1f | ring checks %u, clk in them %u | per post: all %.1f store %.1f publish %.1f\n", e, tr_tiles,
+             tr_posts, tr_clock() - tr_start, (float)(tr_clock() - tr_start) / tr_tiles, (float)tr_wait / tr_tiles, (float)tr_ld / tr_tiles,
+             (float)tr_rel / tr_tiles, (float)tr_tree / tr_tiles, (float)tr_post / tr_tiles, tr_bpn, tr_bp, (float)tr_postonly / (tr_posts ? tr_posts : 1), (float)tr_store / (tr_posts ? tr_posts : 1), (float)tr_pub / (tr_posts ? tr_posts : 1));
+#endif
     __syncwarp();
     if (lane == 0) {
       fence_cta();
@@ -535,11 +617,21 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     }
   } else {
     // ------------------------------------------------------------ insert (warps 2, 3)
-    insert_loop(sh, acc, slog, min_score, warp - 2, lane, cand_counter, dbg);
+    insert_loop(sh, acc, slog, min_score, warp - kInsertWarp0, lane, cand_counter, dbg);
   }
 
   ptx::tcgen05_fence_before();
   __syncthreads();
+#ifdef SMB_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t0 = g_tr[2][32][0];
+    for (int q = 32; q < 44; ++q)
+      printf("tile %2d buf %d | MMA issue %6d..%6d | EPI wait-from %6d t_full %6d released %6d done %6d\n", q, q & 1,
+             (int)(g_tr[0][q][0] - t0), (int)(g_tr[0][q][1] - t0), (int)(g_tr[2][q][0] - t0), (int)(g_tr[2][q][1] - t0),
+             (int)(g_tr[2][q][2] - t0), (int)(g_tr[2][q][3] - t0));
+  }
+#endif
   if (warp == 2) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc_512(tmem_base);

@@ -55,6 +55,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking phase test.  Issued well before its result is needed, its ~90 clk latency (the same an already
+// complete try_wait costs) hides behind whatever the thread does in between.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // try_wait that lets the hardware keep the thread asleep for up to `ns` before reporting failure: the
 // waiting warp stops competing for issue slots / the ALU pipe with the warps doing the epilogue arithmetic.
 __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
@@ -85,6 +100,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
   }
 #endif
+}
+
+// ---------------------------------------------------------------- register reallocation between warpgroups
+// (all four warps of a warpgroup must execute the same instruction; N a multiple of 8)
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ---------------------------------------------------------------- TMA
