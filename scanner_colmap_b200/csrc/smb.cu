@@ -113,6 +113,8 @@ struct smb_handle {
   static constexpr int kUpRing = 64;
   cudaEvent_t up_ev[kUpRing] = {};    // up_ev[t % kUpRing] fires when upload ticket t has landed
   uint64_t up_issued = 0;             // last ticket handed out
+  std::vector<uint32_t> plan_order;   // scratch of match_keys_impl
+  std::vector<uint64_t> plan_ticket;
   uint64_t up_synced = 0;             // tickets <= this are known to have landed
   cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
 
@@ -615,33 +617,67 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   }
   if (npairs > 0x7FFFFFFFull) return give_back(fail(h, SMB_EINVAL, "too many pairs in one call"));
 
+  // uploads that have landed since the last look need no waiting (and no sub-batch of their own)
+  while (h->up_synced < h->up_issued &&
+         cudaEventQuery(h->up_ev[(h->up_synced + 1) % smb_handle::kUpRing]) == cudaSuccess)
+    ++h->up_synced;
+  cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+
   // ---- plan: metas, work items, sub-batches
-  struct Sub { size_t first, last, item0, items, acc, out_cap; };
+  struct Sub { size_t first, last, item0, items, acc, out_cap; uint64_t ticket; };
   std::vector<Sub> subs;
   if (cudaSuccess != h->h_pairs.reserve(npairs)) return give_back(fail(h, SMB_ENOMEM, "pinned allocation failed"));
-  // Sub-batches exist to bound the accumulator footprint.  Splitting further to overlap result copies with
-  // scoring was measured slower (855 pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score
-  // launch pays its own tail), so a call is one sub-batch unless the accumulator budget says otherwise.
+  // Sub-batches exist (a) to bound the accumulator footprint and (b) to start on pairs whose images have landed
+  // while later asynchronous uploads (smb_put_images_async) are still in flight: a new sub-batch begins where
+  // a pair needs a newer, still pending upload ticket than all pairs before it, and each sub-batch's kernels
+  // wait for their own ticket only.  Splitting further to overlap result copies with scoring was measured
+  // slower (855 resident pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score launch pays its
+  // own tail), so with everything resident a call is one sub-batch unless the accumulator budget says otherwise.
   const size_t target_pairs = npairs;
   const size_t sub_budget = h->acc_budget;
   size_t out_cap = 0, n_items_total = 0, max_acc = 0;
-  uint64_t ops = 0, wait_ticket = 0;  // newest asynchronous upload any of the pairs depends on
-  {
-    Sub cur{0, 0, 0, 0, 0, 0};
+  uint64_t ops = 0;
+  // Planned order: with uploads still in flight, pairs are taken in the order their images land (stable), so an
+  // early pair listed after a late one does not wait for the late one's upload.  order[q] = caller index.
+  std::vector<uint32_t>& order = h->plan_order;
+  order.clear();
+  if (h->up_synced < h->up_issued) {
+    std::vector<uint64_t>& tk = h->plan_ticket;
+    tk.resize(npairs);
+    bool sorted = true;
     for (size_t p = 0; p < npairs; ++p) {
       auto i1 = h->images.find(keys[2 * p]);
       auto i2 = h->images.find(keys[2 * p + 1]);
+      uint64_t t = 0;
+      if (i1 != h->images.end() && i2 != h->images.end()) t = std::max(i1->second.up_seq, i2->second.up_seq);
+      tk[p] = t > h->up_synced ? t : 0;
+      if (p && tk[p] < tk[p - 1]) sorted = false;
+    }
+    if (!sorted) {
+      order.resize(npairs);
+      for (size_t p = 0; p < npairs; ++p) order[p] = (uint32_t)p;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return tk[x] < tk[y]; });
+    }
+  }
+  {
+    Sub cur{0, 0, 0, 0, 0, 0, 0};
+    for (size_t p = 0; p < npairs; ++p) {
+      const size_t src = order.empty() ? p : order[p];
+      auto i1 = h->images.find(keys[2 * src]);
+      auto i2 = h->images.find(keys[2 * src + 1]);
       if (i1 == h->images.end() || i2 == h->images.end())
-        return give_back(fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", p,
-                              (unsigned long long)(i1 == h->images.end() ? keys[2 * p] : keys[2 * p + 1])));
+        return give_back(fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", src,
+                              (unsigned long long)(i1 == h->images.end() ? keys[2 * src] : keys[2 * src + 1])));
       const ImageEntry &a = i1->second, &b = i2->second;
-      wait_ticket = std::max(wait_ticket, std::max(a.up_seq, b.up_seq));
+      const uint64_t ticket = std::max(a.up_seq, b.up_seq);
       const size_t need = (size_t)a.n + b.n;
-      if (p > cur.first && (cur.acc + need > sub_budget || p - cur.first >= target_pairs)) {
+      const bool newer_upload = ticket > cur.ticket && ticket > h->up_synced;
+      if (p > cur.first && (cur.acc + need > sub_budget || p - cur.first >= target_pairs || newer_upload)) {
         cur.last = p;
         subs.push_back(cur);
-        cur = Sub{p, 0, cur.item0 + cur.items, 0, 0, 0};
+        cur = Sub{p, 0, cur.item0 + cur.items, 0, 0, 0, cur.ticket};
       }
+      cur.ticket = std::max(cur.ticket, ticket);
       PairMeta& m = h->h_pairs.p[p];
       m.a_row0 = a.row0;
       m.n1 = a.n;
@@ -726,8 +762,6 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   } while (0)
 
   if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
-  if (wait_ticket > h->up_synced)  // tickets complete in order on the upload stream: waiting for the newest is enough
-    SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[wait_ticket % smb_handle::kUpRing], 0));
   SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
   {  // plan upload by a kernel reading pinned host memory (not the copy engine, see fetch_words_kernel)
     static_assert(sizeof(PairMeta) % 4 == 0 && sizeof(WorkItem) % 4 == 0, "plan structs are whole words");
@@ -749,6 +783,9 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
     cudaEvent_t ev_scored = h->ev_pool[4 * k], ev_decided = h->ev_pool[4 * k + 1], ev_s0 = h->ev_pool[4 * k + 2],
                 ev_s1 = h->ev_pool[4 * k + 3];
     TopTwo* acc = h->d_acc.p;  // reused by every sub-batch: all kernels touching it are ordered on the main stream
+    // tickets complete in order on the upload stream: waiting for the newest one of this sub-batch is enough
+    if (sb.ticket > h->up_synced && (k == 0 || sb.ticket > subs[k - 1].ticket))
+      SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[sb.ticket % smb_handle::kUpRing], 0));
     if (sb.acc) SMB_CUDA_R(cudaMemsetAsync(acc, 0, sb.acc * sizeof(TopTwo), st));
     if (sb.items) {
       if (prof) SMB_CUDA_R(cudaEventRecord(ev_s0, st));
@@ -820,7 +857,10 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
     *overflowed = true;
     return give_back(SMB_OK);
   }
-  std::memcpy(res->pair_out.data(), h->h_pair_out.p, npairs * sizeof(PairOut));
+  if (order.empty())
+    std::memcpy(res->pair_out.data(), h->h_pair_out.p, npairs * sizeof(PairOut));
+  else
+    for (size_t q = 0; q < npairs; ++q) res->pair_out[order[q]] = h->h_pair_out.p[q];
   res->total = copied;
   if (prof) {
     float ms = 0.f, score_ms = 0.f;

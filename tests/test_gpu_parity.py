@@ -249,6 +249,25 @@ def test_accumulator_budget_forces_sub_batches(oracle, monkeypatch):
     assert total > 300
 
 
+def test_pairs_are_planned_in_upload_landing_order(oracle):
+    """With uploads in flight one call is split into sub-batches per upload ticket and the pairs are taken in
+    the order their images land; the results must still come back per pair in the CALLER's order."""
+    import torch
+    ids = list(range(12))
+    imgs = [torch.from_numpy(synth.make_image(i, 2048 + 64 * (i % 5), track_step=128)).pin_memory().numpy() for i in ids]
+    pairs = sequential_pairs(ids, 4)
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        order = rng.permutation(len(pairs)) if trial else np.arange(len(pairs))[::-1]
+        scrambled = pairs[order]
+        with SiftMatcher() as m:
+            for k in range(0, 12, 3):                       # four tickets, none synchronised
+                m.put_images_async(ids[k:k + 3], imgs[k:k + 3])
+            _check_pairs(oracle, m, imgs, ids, scrambled)
+            _check_pairs(oracle, m, imgs, ids, scrambled)   # everything landed (or lands): same answer
+            m.synchronize()
+
+
 def test_async_uploads_are_ordered_before_their_pairs(oracle):
     """smb_put_images_async returns at once; a match call must still see every image it names (device-side
     wait on the upload ticket), also across re-puts, evictions and pool growth."""
