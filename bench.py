@@ -221,15 +221,18 @@ def run_ours(args):
     halo_buf = {row: torch.empty(N_DESC * 128, dtype=torch.uint8, device=dev) for row in halo_ids}
 
     def halo_exchange():
-        """Halo rows come straight out of the owning rank's descriptor pool (zero-copy view) over NCCL."""
+        """Halo rows come straight out of the owning rank's descriptor pool (zero-copy view) over NCCL.  Nothing
+        here waits on the host: the receives are queued on torch's stream and adopted with
+        smb_put_images_device_async, so the next match call starts on the pairs that need no halo image and only
+        its last sub-batch waits (on the device) for the exchange."""
         if world == 1:
             return
         def view(row):
             ptr, n = m.image_device_ptr(row)
             return torch.as_tensor(_DevView(ptr, n * 128), device=dev)
         sharding.exchange_halo(sp, view, lambda row: halo_buf[row])
-        torch.cuda.current_stream().synchronize()
-        m.put_images_device(halo_ids, [halo_buf[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids))
+        m.put_images_device_async(halo_ids, [halo_buf[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids),
+                                  torch.cuda.current_stream().cuda_stream)
 
     def barrier():
         if world > 1:

@@ -115,6 +115,14 @@ int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t
 int smb_put_image_device(smb_handle* h, uint32_t image_id, const void* dev_desc, size_t n, size_t d);
 int smb_put_images_device(smb_handle* h, const uint32_t* image_ids, const void* const* dev_descs, const size_t* ns,
                           size_t count, size_t d);
+/* Asynchronous form of smb_put_images_device: the device buffers are (being) produced by work already queued on
+ * `producer_stream` (a cudaStream_t, e.g. the stream an NCCL recv of the halo was launched on; NULL = the legacy
+ * default stream).  The library orders its device-to-device copies after that work on its upload stream and
+ * returns at once; like smb_put_images_async, a match call waits on the device only for the uploads its own pairs
+ * need, so the halo exchange overlaps the matching of every pair that does not touch a halo image.  The buffers
+ * must stay valid and unchanged until smb_synchronize() or until a match call naming the images has returned. */
+int smb_put_images_device_async(smb_handle* h, const uint32_t* image_ids, const void* const* dev_descs,
+                                const size_t* ns, size_t count, size_t d, void* producer_stream);
 int smb_has_image(const smb_handle* h, uint32_t image_id);
 int smb_evict_image(smb_handle* h, uint32_t image_id);
 int smb_clear_images(smb_handle* h);

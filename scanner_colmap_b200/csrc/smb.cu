@@ -113,10 +113,12 @@ struct smb_handle {
   static constexpr int kUpRing = 64;
   cudaEvent_t up_ev[kUpRing] = {};    // up_ev[t % kUpRing] fires when upload ticket t has landed
   uint64_t up_issued = 0;             // last ticket handed out
+  uint64_t up_open = 0;               // ticket whose copies are being queued right now (0 = none)
   std::vector<uint32_t> plan_order;   // scratch of match_keys_impl
   std::vector<uint64_t> plan_ticket;
   uint64_t up_synced = 0;             // tickets <= this are known to have landed
   cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
+  cudaEvent_t ev_ext = nullptr;  // marks the producer stream's position in smb_put_images_device_async
 
   // descriptor pool
   uint8_t* pool = nullptr;
@@ -309,10 +311,13 @@ int alloc_rows(smb_handle* h, uint32_t rows, uint32_t* row0) {
 }
 
 // Everything queued on the upload stream has landed (needed before pool rows are recycled or the pool moves).
+// A ticket that is still being filled (up_open: more copies of it are about to be queued) is NOT marked as
+// landed by this.
 int drain_uploads(smb_handle* h) {
+  const uint64_t done = h->up_open ? h->up_open - 1 : h->up_issued;
   if (h->up_synced != h->up_issued) {
     SMB_CUDA(h, cudaStreamSynchronize(h->stream_up));
-    h->up_synced = h->up_issued;
+    h->up_synced = std::max(h->up_synced, done);
   }
   return SMB_OK;
 }
@@ -345,6 +350,23 @@ int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_
   h->images.emplace(key, e);
   return SMB_OK;
 }
+
+// Marks an upload ticket as "being filled" for the duration of a put call (see drain_uploads).  If the call
+// fails half way the ticket's event is recorded anyway, so nothing can wait on a stale event.
+struct OpenTicket {
+  smb_handle* h;
+  uint64_t ticket;
+  bool recorded = false;
+  OpenTicket(smb_handle* hh, uint64_t t) : h(hh), ticket(t) { h->up_open = t; }
+  cudaError_t finish() {
+    recorded = true;
+    h->up_open = 0;
+    return cudaEventRecord(h->up_ev[ticket % smb_handle::kUpRing], h->stream_up);
+  }
+  ~OpenTicket() {
+    if (!recorded) finish();
+  }
+};
 
 smb_result* acquire_result(smb_handle* h) {
   if (!h->result_pool.empty()) {
@@ -421,6 +443,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
   for (auto& e : h->up_ev) SMB_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
   for (auto& e : h->ev) SMB_CUDA_C(cudaEventCreate(&e));
   {
     void* fn = nullptr;
@@ -485,6 +508,7 @@ void smb_destroy(smb_handle* h) {
   if (h->stream_up) cudaStreamDestroy(h->stream_up);
   for (auto& e : h->up_ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   delete h;
 }
 
@@ -524,11 +548,12 @@ int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t
   if (h->up_issued - h->up_synced >= (uint64_t)smb_handle::kUpRing - 1)  // the event ring is about to wrap
     if (int rc = drain_uploads(h)) return rc;
   const uint64_t ticket = ++h->up_issued;
+  OpenTicket open(h, ticket);
   for (size_t k = 0; k < count; ++k) {
     int rc = put_image_impl(h, image_ids[k], descs[k], ns[k], d, cudaMemcpyHostToDevice, h->stream_up, ticket);
     if (rc != SMB_OK) return rc;
   }
-  SMB_CUDA(h, cudaEventRecord(h->up_ev[ticket % smb_handle::kUpRing], h->stream_up));
+  SMB_CUDA(h, open.finish());
   return SMB_OK;
 }
 
@@ -551,6 +576,26 @@ int smb_put_images_device(smb_handle* h, const uint32_t* image_ids, const void* 
     if (rc != SMB_OK) return rc;
   }
   SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMB_OK;
+}
+
+int smb_put_images_device_async(smb_handle* h, const uint32_t* image_ids, const void* const* dev_descs,
+                                const size_t* ns, size_t count, size_t d, void* producer_stream) {
+  if (!h) return SMB_EINVAL;
+  if (count && (!image_ids || !dev_descs || !ns)) return fail(h, SMB_EINVAL, "null array argument");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  if (h->up_issued - h->up_synced >= (uint64_t)smb_handle::kUpRing - 1)  // the event ring is about to wrap
+    if (int rc = drain_uploads(h)) return rc;
+  const uint64_t ticket = ++h->up_issued;
+  OpenTicket open(h, ticket);
+  // the copies below must not start before the producer's queued work (e.g. the NCCL recv) has finished
+  SMB_CUDA(h, cudaEventRecord(h->ev_ext, static_cast<cudaStream_t>(producer_stream)));
+  SMB_CUDA(h, cudaStreamWaitEvent(h->stream_up, h->ev_ext, 0));
+  for (size_t k = 0; k < count; ++k) {
+    int rc = put_image_impl(h, image_ids[k], dev_descs[k], ns[k], d, cudaMemcpyDefault, h->stream_up, ticket);
+    if (rc != SMB_OK) return rc;
+  }
+  SMB_CUDA(h, open.finish());
   return SMB_OK;
 }
 

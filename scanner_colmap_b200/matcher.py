@@ -75,6 +75,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_put_images_async.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_image_device.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_size_t]
     L.smb_put_images_device.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t]
+    L.smb_put_images_device_async.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp]
     L.smb_has_image.argtypes = [vp, ctypes.c_uint32]
     L.smb_evict_image.argtypes = [vp, ctypes.c_uint32]
     L.smb_clear_images.argtypes = [vp]
@@ -200,6 +201,18 @@ class SiftMatcher:
         cnt = (ctypes.c_size_t * n)(*[int(x) for x in ns])
         self._check(self._L.smb_put_images_device(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
                                                   ctypes.cast(cnt, ctypes.c_void_p), n, 128))
+
+    def put_images_device_async(self, image_ids: Sequence[int], dev_ptrs: Sequence[int], ns: Sequence[int],
+                                producer_stream: int = 0) -> None:
+        """Adopt device buffers that work already queued on `producer_stream` (a cudaStream_t handle, e.g.
+        torch.cuda.current_stream().cuda_stream after an NCCL recv) is still filling; returns at once."""
+        n = len(dev_ptrs)
+        ids = np.asarray(list(image_ids), dtype=np.uint32)
+        ptrs = (ctypes.c_void_p * n)(*[int(p) for p in dev_ptrs])
+        cnt = (ctypes.c_size_t * n)(*[int(x) for x in ns])
+        self._check(self._L.smb_put_images_device_async(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
+                                                        ctypes.cast(cnt, ctypes.c_void_p), n, 128,
+                                                        ctypes.c_void_p(int(producer_stream))))
 
     def has_image(self, image_id: int) -> bool:
         return bool(self._L.smb_has_image(self._h, int(image_id)))

@@ -268,6 +268,28 @@ def test_pairs_are_planned_in_upload_landing_order(oracle):
             m.synchronize()
 
 
+def test_device_buffers_adopted_behind_their_producer_stream(oracle):
+    """smb_put_images_device_async: the buffers are still being written by work queued on another stream (the
+    halo recv in the multi-GPU path); pairs that name them must wait for it, the others need not."""
+    import torch
+    ids = list(range(6))
+    imgs = [synth.make_image(i, 2304 + 128 * i, track_step=128) for i in ids]
+    side = torch.cuda.Stream()
+    with SiftMatcher() as m:
+        m.put_images(ids[:4], imgs[:4])
+        bufs = [torch.zeros(im.size, dtype=torch.uint8, device="cuda") for im in imgs[4:]]
+        host = [torch.from_numpy(im.reshape(-1)).pin_memory() for im in imgs[4:]]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(20_000_000)                      # ~10 ms: the buffers are still zero when adopted
+            for b, hbuf in zip(bufs, host):
+                b.copy_(hbuf, non_blocking=True)
+        m.put_images_device_async(ids[4:], [b.data_ptr() for b in bufs], [im.shape[0] for im in imgs[4:]],
+                                  side.cuda_stream)
+        _check_pairs(oracle, m, imgs, ids, np.array([[4, 5], [0, 1], [3, 4], [1, 2], [2, 5]], dtype=np.uint32))
+        m.synchronize()
+
+
 def test_async_uploads_are_ordered_before_their_pairs(oracle):
     """smb_put_images_async returns at once; a match call must still see every image it names (device-side
     wait on the upload ticket), also across re-puts, evictions and pool growth."""
