@@ -331,8 +331,11 @@ int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_
   auto old = h->images.find(key);
   if (old != h->images.end()) {
     // pairs already queued on the stream may still read the old rows; a pending upload may still write them
+    // (only then is the upload stream drained: draining it for every image of a device-async call would wait
+    // for that call's own producer, e.g. the halo recv, on the host)
     SMB_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (int rc = drain_uploads(h)) return rc;
+    if (old->second.up_seq > h->up_synced)
+      if (int rc = drain_uploads(h)) return rc;
     free_rows(h, old->second.row0, old->second.rows);
     h->images.erase(old);
   }

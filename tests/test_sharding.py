@@ -12,7 +12,8 @@ import torch.multiprocessing as mp
 from scanner_colmap_b200 import sequential_pairs, sharding, synth
 
 
-@pytest.mark.parametrize("n,overlap,world", [(100, 10, 1), (100, 10, 2), (1000, 20, 8), (37, 10, 4), (5, 10, 4), (3, 4, 8)])
+@pytest.mark.parametrize("n,overlap,world", [(100, 10, 1), (100, 10, 2), (1000, 20, 8), (37, 10, 4), (5, 10, 4), (3, 4, 8),
+                                             (200, 201, 8), (24, 24, 3)])  # the last two: exhaustive (configs[4])
 def test_plans_cover_every_pair_exactly_once(n, overlap, world):
     sizes = [8192] * n
     want = {tuple(p) for p in sequential_pairs(list(range(n)), overlap).tolist()}

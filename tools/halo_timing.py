@@ -18,6 +18,9 @@ def ex():
     sharding.exchange_halo(sp, view, lambda r: buf[r]); torch.cuda.current_stream().synchronize()
 def put():
     if halo: m.put_images_device(halo, [buf[r].data_ptr() for r in halo], [8192] * len(halo))
+def ex_async():
+    sharding.exchange_halo(sp, view, lambda r: buf[r])
+    if halo: m.put_images_device_async(halo, [buf[r].data_ptr() for r in halo], [8192] * len(halo), torch.cuda.current_stream().cuda_stream)
 for _ in range(3): ex(); put(); m.match_pairs_count(sp.pairs)
 ts = {"exchange": [], "put": [], "match": [], "barrier": []}
 for _ in range(10):
@@ -25,4 +28,16 @@ for _ in range(10):
     ex(); t2 = time.perf_counter(); put(); t3 = time.perf_counter(); m.match_pairs_count(sp.pairs); t4 = time.perf_counter()
     for k, v in zip(ts, (t2 - t1, t3 - t2, t4 - t3, t1 - t0)): ts[k].append(v * 1e3)
 print(f"rank {rank}: own {len(own)} halo {len(halo)} pairs {len(sp.pairs)} " + " ".join(f"{k}={np.median(v):.3f}ms" for k, v in ts.items()), flush=True)
+ta = {"enqueue": [], "match": []}
+for _ in range(3): ex_async(); m.match_pairs_count(sp.pairs)
+for _ in range(10):
+    dist.barrier(); torch.cuda.synchronize(); t1 = time.perf_counter()
+    ex_async(); t2 = time.perf_counter(); m.match_pairs_count(sp.pairs); t3 = time.perf_counter()
+    ta["enqueue"].append((t2 - t1) * 1e3); ta["match"].append((t3 - t2) * 1e3)
+print(f"rank {rank} async: " + " ".join(f"{k}={np.median(v):.3f}ms" for k, v in ta.items()), flush=True)
+m.clear_images(); m.put_images(own, imgs); ex(); put()
+tm = []
+for _ in range(10):
+    dist.barrier(); torch.cuda.synchronize(); t1 = time.perf_counter(); m.match_pairs_count(sp.pairs); tm.append((time.perf_counter() - t1) * 1e3)
+print(f"rank {rank} resident halo, match only: {np.median(tm):.3f}ms", flush=True)
 dist.barrier(); dist.destroy_process_group()
