@@ -37,13 +37,17 @@ struct PairMeta {
   uint32_t out_slot; // index into the per-call pair_out array
 };
 
-struct WorkItem {     // one strip (<= 256 rows) of image 1 against all of image 2
-  uint32_t a_row;     // pool row of the strip
-  uint32_t b_row;     // pool row of image 2
-  uint32_t n_btiles;  // number of 256-column tiles
-  uint32_t pair;      // index into PairMeta (batch-local)
-  uint32_t m_tiles;   // 1 or 2 accumulator row blocks (128 rows each) in this strip
+struct alignas(16) WorkItem {  // one strip (<= 256 rows) of image 1 against all of image 2
+  uint32_t a_row;      // pool row of the strip
+  uint32_t b_row;      // pool row of image 2
+  uint32_t n_btiles;   // number of 256-column tiles
+  uint32_t m_tiles;    // 1 or 2 accumulator row blocks (128 rows each) in this strip
+  uint32_t row_slot0;  // accumulator slot of the strip's first row   (= acc_off + a_row - a_row0)
+  uint32_t col_slot0;  // accumulator slot of image 2's first column  (= acc_off + n1)
+  uint32_t pair;       // index into PairMeta (batch-local)
+  uint32_t pad_;
 };
+static_assert(sizeof(WorkItem) == 32, "WorkItem is two 16-byte words");
 
 struct TopTwo {
   unsigned long long k1;  // best key
@@ -481,12 +485,15 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     uint32_t tr_wait = 0, tr_ld = 0, tr_rel = 0, tr_tree = 0, tr_post = 0, tr_tiles = 0, tr_posts = 0, tr_bp = 0, tr_bpn = 0, tr_store = 0, tr_pub = 0, tr_postonly = 0;
     const uint32_t tr_start = tr_clock();
 #endif
+    WorkItem w_next = blockIdx.x < n_items ? items[blockIdx.x] : WorkItem{};
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const WorkItem w = items[it];
-      const PairMeta pm = pairs[w.pair];
+      const WorkItem w = w_next;
+      // the next item's descriptor is fetched a whole item ahead (everything this warp needs is in the WorkItem
+      // itself, so there is no dependent PairMeta load on the tile pipeline's critical warp)
+      if (it + gridDim.x < n_items) w_next = items[it + gridDim.x];
       // accumulator slot of this thread's row (mh = 0) and of this warp's first column
-      const uint32_t row_slot = pm.acc_off + (w.a_row - pm.a_row0) + quarter * 32 + lane;
-      const uint32_t col_slot0 = pm.acc_off + pm.n1 + col0;
+      const uint32_t row_slot = w.row_slot0 + quarter * 32 + lane;
+      const uint32_t col_slot0 = w.col_slot0 + col0;
       for (uint32_t t = 0; t < w.n_btiles; ++t) {
         for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
 #ifdef SMB_TRACE

@@ -791,7 +791,8 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
       if (!m.n1 || !m.n2) continue;
       const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
       for (uint32_t r = 0; r < m.n1; r += kStripRows)
-        it0[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, (uint32_t)(p - sb.first), m.n1 - r > (uint32_t)kMTile ? 2u : 1u};
+        it0[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, m.n1 - r > (uint32_t)kMTile ? 2u : 1u,
+                             m.acc_off + r, m.acc_off + m.n1, (uint32_t)(p - sb.first), 0u};
     }
     bool uniform = true;
     for (size_t x = 1; x < ni && uniform; ++x) uniform = it0[x].n_btiles == it0[0].n_btiles;
