@@ -275,14 +275,15 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- end to end through the public API: host (pinned) descriptors in, matches out, every step.
-    # The images are uploaded asynchronously in 4 chunks (a short first one, so matching can start early) and
+    # The images are uploaded asynchronously in 3 chunks (a short first one, so matching can start early) and
     # ONE match_pairs call follows: the library takes the pairs in the order their images land, one sub-batch
     # per upload ticket, each waiting on the device for its own ticket only -- so the copy of chunk k+1 overlaps
     # the matching of chunk k without any host round trip in between.
     n_own = len(own_ids)
-    first = min(n_own, OVERLAP + 2)
-    bounds = [0, first] + [first + ((n_own - first) * c) // 3 for c in (1, 2, 3)]
-    bounds = sorted(set(bounds))
+    # chunk sizes grow so that the upload of chunk k+1 (~55 GB/s) hides under the matching of chunk k: 16 / 24 / 60
+    # images of 100 measured best (tools/e2e_chunks.py)
+    first = min(n_own, OVERLAP + 6)
+    bounds = sorted(set([0, first, max(first, (2 * n_own) // 5), n_own]))
     n_chunks = len(bounds) - 1
 
     def e2e_step():
@@ -367,7 +368,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 4 chunks) + "
+                    "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 3 chunks) + "
                             "one match_pairs call (sub-batches wait on the device for their own upload; matches land "
                             "in pinned host memory)"},
             "gpu_launches": int(launches),

@@ -12,8 +12,8 @@ def T(f, n=10):
     m.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 m.put_images(ids, imgs)
 print("match all (resident) %.3f ms" % T(lambda: m.match_pairs_count(pairs)))
-for bounds in ([0, 25, 50, 75, 100], [0, 12, 40, 70, 100], [0, 11, 33, 66, 100], [0, 11, 55, 100], [0, 16, 58, 100], [0, 11, 100],
-               [0, 11, 30, 53, 76, 100], [0, 8, 20, 40, 60, 80, 100]):
+for bounds in ([0, 16, 40, 100], [0, 14, 36, 100], [0, 18, 45, 100], [0, 20, 50, 100], [0, 16, 36, 64, 100], [0, 16, 48, 100],
+               [0, 14, 30, 56, 100], [0, 24, 56, 100]):
     n = len(bounds) - 1
     groups = [[] for _ in range(n)]
     for a, b in pairs.tolist():
@@ -25,4 +25,8 @@ for bounds in ([0, 25, 50, 75, 100], [0, 12, 40, 70, 100], [0, 11, 33, 66, 100],
         for c in range(n): m.put_images_async(ids[bounds[c]:bounds[c + 1]], imgs[bounds[c]:bounds[c + 1]])
         for g in groups:
             if len(g): m.match_pairs_count(g)
-    print(bounds, [len(g) for g in groups], "e2e %.3f ms" % T(step), flush=True)
+    def step1():
+        m.clear_images()
+        for c in range(n): m.put_images_async(ids[bounds[c]:bounds[c + 1]], imgs[bounds[c]:bounds[c + 1]])
+        m.match_pairs_count(pairs)
+    print(bounds, [len(g) for g in groups], "e2e per-chunk calls %.3f ms, one call %.3f ms" % (T(step), T(step1)), flush=True)
