@@ -282,8 +282,13 @@ def run_ours(args):
     n_own = len(own_ids)
     # chunk sizes grow so that the upload of chunk k+1 (~55 GB/s) hides under the matching of chunk k: 16 / 24 / 60
     # images of 100 measured best (tools/e2e_chunks.py)
-    first = min(n_own, OVERLAP + 6)
-    bounds = sorted(set([0, first, max(first, (2 * n_own) // 5), n_own]))
+    # (with 8 ranks uploading at once the host link is slower and a shorter first chunk + four chunks measured better)
+    if world == 1:
+        first = min(n_own, OVERLAP + 6)
+        bounds = sorted(set([0, first, max(first, (2 * n_own) // 5), n_own]))
+    else:
+        first = min(n_own, OVERLAP + 2)
+        bounds = sorted(set([0, first] + [first + ((n_own - first) * c) // 3 for c in (1, 2, 3)]))
     n_chunks = len(bounds) - 1
 
     def e2e_step():
@@ -368,7 +373,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 3 chunks) + "
+                    "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 3-4 chunks) + "
                             "one match_pairs call (sub-batches wait on the device for their own upload; matches land "
                             "in pinned host memory)"},
             "gpu_launches": int(launches),
