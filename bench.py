@@ -218,20 +218,26 @@ def run_ours(args):
     m = SiftMatcher(device=local, profile=True)
     stream = torch.cuda.ExternalStream(m.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    halo_buf = {row: torch.empty(N_DESC * 128, dtype=torch.uint8, device=dev) for row in halo_ids}
+    halo_src = {}                                     # one contiguous receive buffer per owning rank
+    for row, src in sp.recv:
+        halo_src[src] = halo_src.get(src, 0) + N_DESC * 128
+    halo_src = {src: torch.empty(nb, dtype=torch.uint8, device=dev) for src, nb in halo_src.items()}
 
     def halo_exchange():
-        """Halo rows come straight out of the owning rank's descriptor pool (zero-copy view) over NCCL.  Nothing
-        here waits on the host: the receives are queued on torch's stream and adopted with
+        """Halo rows come straight out of the owning rank's descriptor pool over NCCL, one message per peer
+        (a zero-copy view of the pool when the rows are adjacent there, which they are for whole 256-row images).
+        Nothing here waits on the host: the receives are queued on torch's stream and adopted with
         smb_put_images_device_async, so the next match call starts on the pairs that need no halo image and only
         its last sub-batch waits (on the device) for the exchange."""
         if world == 1:
             return
-        def view(row):
-            ptr, n = m.image_device_ptr(row)
-            return torch.as_tensor(_DevView(ptr, n * 128), device=dev)
-        sharding.exchange_halo(sp, view, lambda row: halo_buf[row])
-        m.put_images_device_async(halo_ids, [halo_buf[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids),
+        def send_span(rows):
+            spans = [m.image_device_ptr(r) for r in rows]
+            if all(spans[k][0] + spans[k][1] * 128 == spans[k + 1][0] for k in range(len(spans) - 1)):
+                return torch.as_tensor(_DevView(spans[0][0], sum(n for _, n in spans) * 128), device=dev)
+            return torch.cat([torch.as_tensor(_DevView(ptr, n * 128), device=dev) for ptr, n in spans])
+        got = sharding.exchange_halo_packed(sp, lambda row: N_DESC * 128, send_span, lambda src, nb: halo_src[src])
+        m.put_images_device_async(halo_ids, [got[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids),
                                   torch.cuda.current_stream().cuda_stream)
 
     def barrier():

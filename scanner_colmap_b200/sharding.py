@@ -87,3 +87,34 @@ def exchange_halo(p: ShardPlan, get_tensor: Callable[[int], "object"], make_recv
         for r in dist.batch_isend_irecv(ops):
             r.wait()
     return out
+
+
+def exchange_halo_packed(p: ShardPlan, row_bytes: Callable[[int], int], get_send: Callable[[List[int]], "object"],
+                         make_recv: Callable[[int, int], "object"], group=None) -> dict:
+    """Same exchange with ONE message per peer instead of one per image (queuing 18 point-to-point operations
+    through torch.distributed costs 0.2-0.45 ms of host time per step on 8 GPUs).  ``get_send(rows)`` returns a
+    1-D uint8 tensor holding those rows back to back (a zero-copy view when they are adjacent in the descriptor
+    pool, a packed copy otherwise); ``make_recv(src, nbytes)`` returns the 1-D uint8 receive buffer for everything
+    coming from rank ``src``.  Returns {row: 1-D view of that row's bytes inside its receive buffer}.  Both sides
+    derive the message sizes from the plan alone, so they always agree."""
+    import torch.distributed as dist
+    by_dst, by_src = {}, {}
+    for row, dst in p.send:
+        by_dst.setdefault(dst, []).append(row)
+    for row, src in p.recv:
+        by_src.setdefault(src, []).append(row)
+    ops, out = [], {}
+    for dst in sorted(by_dst):
+        ops.append(dist.P2POp(dist.isend, get_send(by_dst[dst]), dst, group=group))
+    for src in sorted(by_src):
+        rows = by_src[src]
+        buf = make_recv(src, sum(row_bytes(r) for r in rows))
+        off = 0
+        for r in rows:
+            out[r] = buf[off:off + row_bytes(r)]
+            off += row_bytes(r)
+        ops.append(dist.P2POp(dist.irecv, buf, src, group=group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return out

@@ -55,6 +55,11 @@ def _worker(rank, world, port, n, overlap, q):
                                      lambda row: torch.empty(sizes[row] * 128, dtype=torch.uint8))
         ok = all(np.array_equal(got[row].numpy().reshape(-1, 128), synth.make_image(row, sizes[row], track_step=4))
                  for row, _ in p.recv)
+        # one message per peer: same bytes, views into one receive buffer per source
+        got2 = sharding.exchange_halo_packed(p, lambda row: sizes[row] * 128,
+                                             lambda rows: torch.cat([own[r].reshape(-1) for r in rows]),
+                                             lambda src, nbytes: torch.empty(nbytes, dtype=torch.uint8))
+        ok = ok and sorted(got2) == sorted(got) and all(torch.equal(got2[row], got[row]) for row in got)
         q.put((rank, ok, len(p.recv), len(p.send), len(p.pairs)))
     finally:
         dist.destroy_process_group()
