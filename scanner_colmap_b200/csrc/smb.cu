@@ -11,6 +11,7 @@
 #include "../../include/smb.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -150,6 +151,10 @@ struct smb_handle {
   std::vector<smb_result*> result_pool;
   smb_timing timing{};
   size_t acc_budget = (size_t)64 << 20;  // accumulator slots per internal batch (16 B each; must stay < 2^32)
+  // Result-copy overlap (see match_keys_impl): what the last calls measured
+  double d2h_ms_per_mb = 0.0;            // device-to-host rate of the match copies (moving average)
+  double matches_per_pair = 0.0;         // matches per pair of the last call
+  double split_ms = 0.5;                 // split a call in two when its predicted match copy takes longer
 
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   uint32_t dbg_flags = 0;  // SMB_DEBUG_FLAGS: bring-up timing experiments (see score_tcgen05_kernel)
@@ -426,6 +431,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
+  if (const char* e = getenv("SMB_RESULT_SPLIT_MS")) h->split_ms = atof(e);  // tests: 0 = always split, <0 = never
   if (const char* e = getenv("SMB_ACC_BUDGET")) h->acc_budget = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 0));  // tests: force sub-batches
   int rc = SMB_OK;
   auto bail = [&](int code) {
@@ -681,7 +687,16 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   // wait for their own ticket only.  Splitting further to overlap result copies with scoring was measured
   // slower (855 resident pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score launch pays its
   // own tail), so with everything resident a call is one sub-batch unless the accumulator budget says otherwise.
-  const size_t target_pairs = npairs;
+  // Exception, decided from measurements: when the device-to-host copy of the matches is slow (several ranks
+  // sharing the host links: 12-20 GB/s per GPU were observed with eight ranks against 52 GB/s alone), the first
+  // 80 % of the pairs form their own sub-batch, so their matches cross PCIe under the scoring of the rest.  The
+  // extra launches cost ~0.2 ms (runner-up, decide and the accumulator reset sit between the two score kernels),
+  // so this only happens once the predicted copy time exceeds split_ms.
+  size_t target_pairs = npairs;
+  if (h->split_ms >= 0.0 && npairs >= 64) {
+    const double pred_ms = h->matches_per_pair * (double)npairs * sizeof(smb_match) * 1e-6 * h->d2h_ms_per_mb;
+    if (pred_ms > h->split_ms || h->split_ms == 0.0) target_pairs = (npairs * 4 + 4) / 5;
+  }
   const size_t sub_budget = h->acc_budget;
   size_t out_cap = 0, n_items_total = 0, max_acc = 0;
   uint64_t ops = 0;
@@ -877,7 +892,8 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   }
 
   // ---- results: as each sub-batch's header lands, copy exactly the matches it produced
-  size_t copied = 0;
+  size_t copied = 0, last_copy_bytes = 0;
+  std::chrono::steady_clock::time_point last_copy_t0{};
   for (size_t k = 0; k < subs.size(); ++k) {
     SMB_CUDA_R(cudaEventSynchronize(h->ev_pool[4 * k + 1]));
     const size_t upto = (size_t)h->h_sub_counters.p[4 * k];  // decide kernels reserve contiguously, in stream order
@@ -896,11 +912,20 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
     if (upto > copied)
       SMB_CUDA_R(cudaMemcpyAsync(res->matches + copied, h->d_out.p + copied, (upto - copied) * sizeof(smb_match),
                                  cudaMemcpyDeviceToHost, so));
+    if (k + 1 == subs.size()) {
+      last_copy_bytes = (upto - copied) * sizeof(smb_match);
+      last_copy_t0 = std::chrono::steady_clock::now();
+    }
     copied = upto;
   }
   if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[1], so));
   SMB_CUDA_R(cudaStreamSynchronize(so));
   SMB_CUDA_R(cudaStreamSynchronize(st));
+  if (last_copy_bytes >= (1u << 20)) {  // the copy just waited for: header of the last sub-batch -> all matches landed
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - last_copy_t0).count();
+    const double rate = ms / (last_copy_bytes * 1e-6);
+    h->d2h_ms_per_mb = h->d2h_ms_per_mb > 0.0 ? 0.75 * h->d2h_ms_per_mb + 0.25 * rate : rate;
+  }
   const unsigned long long* last = h->h_sub_counters.p + 4 * (subs.size() - 1);
   if (last[3]) {  // the survivor log overflowed: this attempt's runner-up keys are incomplete
     *overflowed = true;
@@ -911,6 +936,7 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   else
     for (size_t q = 0; q < npairs; ++q) res->pair_out[order[q]] = h->h_pair_out.p[q];
   res->total = copied;
+  h->matches_per_pair = (double)copied / (double)npairs;
   if (prof) {
     float ms = 0.f, score_ms = 0.f;
     SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));

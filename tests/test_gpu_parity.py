@@ -249,6 +249,20 @@ def test_accumulator_budget_forces_sub_batches(oracle, monkeypatch):
     assert total > 300
 
 
+def test_result_copy_overlap_split_is_invisible(oracle, monkeypatch):
+    """When the match copy is predicted to be slow the first 80 % of the pairs become their own sub-batch
+    (SMB_RESULT_SPLIT_MS=0 forces it); per-pair results must not change."""
+    ids = list(range(24))
+    imgs = [synth.make_image(i, 700 + 29 * (i % 7), track_step=32) for i in ids]
+    pairs = sequential_pairs(ids, 5)                    # 86 pairs >= 64
+    monkeypatch.setenv("SMB_RESULT_SPLIT_MS", "0")
+    with SiftMatcher(profile=True) as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+        assert m.timing()["score_launches"] == 2
+    assert total > 300
+
+
 def test_pairs_are_planned_in_upload_landing_order(oracle):
     """With uploads in flight one call is split into sub-batches per upload ticket and the pairs are taken in
     the order their images land; the results must still come back per pair in the CALLER's order."""
