@@ -154,7 +154,7 @@ struct smb_handle {
   // Result-copy overlap (see match_keys_impl): what the last calls measured
   double d2h_ms_per_mb = 0.0;            // device-to-host rate of the match copies (moving average)
   double matches_per_pair = 0.0;         // matches per pair of the last call
-  double split_ms = 0.5;                 // split a call in two when its predicted match copy takes longer
+  double split_ms = -1.0;                // split a call in two when its predicted match copy takes longer (< 0: never)
 
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   uint32_t dbg_flags = 0;  // SMB_DEBUG_FLAGS: bring-up timing experiments (see score_tcgen05_kernel)
@@ -431,7 +431,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
-  if (const char* e = getenv("SMB_RESULT_SPLIT_MS")) h->split_ms = atof(e);  // tests: 0 = always split, <0 = never
+  if (const char* e = getenv("SMB_RESULT_SPLIT_MS")) h->split_ms = atof(e);  // 0 = always split (tests), <0 = never
   if (const char* e = getenv("SMB_ACC_BUDGET")) h->acc_budget = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 0));  // tests: force sub-batches
   int rc = SMB_OK;
   auto bail = [&](int code) {
@@ -687,11 +687,12 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
   // wait for their own ticket only.  Splitting further to overlap result copies with scoring was measured
   // slower (855 resident pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score launch pays its
   // own tail), so with everything resident a call is one sub-batch unless the accumulator budget says otherwise.
-  // Exception, decided from measurements: when the device-to-host copy of the matches is slow (several ranks
-  // sharing the host links: 12-20 GB/s per GPU were observed with eight ranks against 52 GB/s alone), the first
-  // 80 % of the pairs form their own sub-batch, so their matches cross PCIe under the scoring of the rest.  The
-  // extra launches cost ~0.2 ms (runner-up, decide and the accumulator reset sit between the two score kernels),
-  // so this only happens once the predicted copy time exceeds split_ms.
+  // Optional exception (SMB_RESULT_SPLIT_MS=<ms>, off by default): when the predicted device-to-host copy of the
+  // matches exceeds that many milliseconds -- from the copy rate and matches per pair the previous calls measured --
+  // the first 80 % of the pairs form their own sub-batch, so their matches cross PCIe under the scoring of the
+  // rest.  Measured on 8 GPUs with a 0.5 ms threshold: 1.073 M vs 1.075 M pairs/s, i.e. no gain (the extra
+  // launches cost ~0.2 ms: runner-up, decide and the accumulator reset sit between the two score kernels), hence
+  // off; kept because it is the cheap answer where result copies do dominate (many matches per pair, slow links).
   size_t target_pairs = npairs;
   if (h->split_ms >= 0.0 && npairs >= 64) {
     const double pred_ms = h->matches_per_pair * (double)npairs * sizeof(smb_match) * 1e-6 * h->d2h_ms_per_mb;
