@@ -1,0 +1,40 @@
+"""bench.py's JSON contract, as far as it can be checked without a GPU: the reference arm (CPU restatement on the
+host cores) runs anywhere; the product arm must refuse to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, timeout=600):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=timeout, cwd=ROOT)
+
+
+def test_reference_arm_prints_the_contract_line(built):
+    out = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                   # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "pairs/sec at 8192 SIFT/img" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] >= 3
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = _run("--steps", "1", "--warmup", "1", timeout=300)
+    assert out.returncode != 0
+    assert "no CUDA device" in (out.stderr + out.stdout)
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]   # and prints no number
