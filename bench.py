@@ -356,7 +356,7 @@ def run_ours(args):
             from oracle import oracle
             oracle.build()
             cores = oracle.num_procs()
-            sample = 2 * cores
+            sample = 4 * cores                     # ~10 s of CPU work on the 16-core box
             v, used, dt, _ = cpu_sample(sample)
             cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": f"{sample} of the workload's 8192x8192 pairs, {dt:.1f} s on {used} threads "
