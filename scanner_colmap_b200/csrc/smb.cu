@@ -879,7 +879,7 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
     }
     decide_kernel<<<(unsigned)(sb.last - sb.first), kDecideThreads, 0, st>>>(h->d_pairs.p + sb.first, acc, h->lut_dev,
                                                                              h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
-                                                                             h->d_out.p, h->d_counters, h->d_pair_out.p);
+                                                                             h->d_out.p, ~0ull, h->d_counters, h->d_counters + 3, h->d_pair_out.p);
     SMB_CUDA_R(cudaGetLastError());
     h->timing.total_launches++;
     SMB_CUDA_R(cudaEventRecord(ev_scored, st));

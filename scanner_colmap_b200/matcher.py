@@ -56,7 +56,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SMB_LIB") or LIB_PATH   # SMB_LIB: A/B a build variant (tools/bin/*.so) under the tests
     if not os.path.exists(p):
         raise SmbError(SMB_ENODEVICE, f"{p} not built -- run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = ctypes.CDLL(p)

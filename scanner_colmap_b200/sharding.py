@@ -5,6 +5,11 @@ the table is cut into contiguous anchor windows: rank g owns anchor images ``[s_
 the descriptors of the ``overlap - 1`` images after ``e_g`` (its halo), which live in the next rank's (ranks')
 HBM and are fetched peer-to-peer (``torch.distributed`` send/recv: NCCL over NVLink on GPUs, gloo in the CPU
 tests).  There is no reduction and no other collective; match lists go back to the host per rank.
+
+Exhaustive matching (every image against every later image, BASELINE configs[4]) has no window to cut: there the
+upper triangle of the pair matrix is tiled in 2-D over image blocks (``plan_exhaustive``), tiles are dealt to
+the ranks by cost, and a rank needs only the blocks its tiles touch (half of the descriptors on 8 GPUs) instead
+of an all-gather of everything.
 """
 from __future__ import annotations
 
@@ -118,3 +123,112 @@ def exchange_halo_packed(p: ShardPlan, row_bytes: Callable[[int], int], get_send
         for r in dist.batch_isend_irecv(ops):
             r.wait()
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Exhaustive matching: 2-D tiling of the upper-triangular pair matrix
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class ExhaustivePlan:
+    rank: int
+    world: int
+    own: Tuple[int, int]                     # rows this rank uploads from the host (contiguous, balanced on bytes)
+    blocks: List[Tuple[int, int]]            # the image blocks [s, e) of the tiling (same on every rank)
+    tiles: List[Tuple[int, int]]             # (block i, block j), i <= j, assigned to this rank
+    need: List[int]                          # every row this rank's tiles touch (ascending)
+    recv: List[Tuple[int, int]]              # (row, owner rank): needed but not owned, ascending row
+    send: List[Tuple[int, int]]              # (row, destination rank), ascending (row, destination)
+    pairs: np.ndarray                        # uint32 [m, 2] (row1 < row2) this rank matches
+    cost: float                              # sum n1*n2 over this rank's pairs
+    imbalance: float                         # max over ranks / mean over ranks of cost (same on every rank)
+    resident_fraction: float                 # largest share of all descriptor bytes any rank must hold
+
+
+def _balanced_cuts(weights: np.ndarray, parts: int) -> List[Tuple[int, int]]:
+    """Contiguous ranges with near-equal weight sums (ranges may be empty when parts > len(weights))."""
+    n = len(weights)
+    acc = np.concatenate([[0.0], np.cumsum(weights, dtype=np.float64)])
+    cuts = [0]
+    for g in range(1, parts):
+        c = int(np.searchsorted(acc, acc[-1] * g / parts, side="left")) if acc[-1] > 0 else round(n * g / parts)
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[g], cuts[g + 1]) for g in range(parts)]
+
+
+def _tile_cost(sz: np.ndarray, pre: np.ndarray, pre2: np.ndarray, bi: Tuple[int, int], bj: Tuple[int, int]) -> float:
+    """sum of n_i * n_j over the pairs i < j of tile (bi, bj); bi == bj is a diagonal tile."""
+    si = pre[bi[1]] - pre[bi[0]]
+    if bi == bj:
+        return 0.5 * (si * si - (pre2[bi[1]] - pre2[bi[0]]))
+    return si * (pre[bj[1]] - pre[bj[0]])
+
+
+def _assign_tiles(sizes: np.ndarray, world: int, nblocks: int):
+    sz = sizes.astype(np.float64)
+    pre = np.concatenate([[0.0], np.cumsum(sz)])
+    pre2 = np.concatenate([[0.0], np.cumsum(sz * sz)])
+    blocks = [b for b in _balanced_cuts(sz, nblocks) if b[1] > b[0]]
+    nb = len(blocks)
+    tiles = [(i, j) for i in range(nb) for j in range(i, nb)]
+    cost = {t: _tile_cost(sz, pre, pre2, blocks[t[0]], blocks[t[1]]) for t in tiles}
+    tiles = [t for t in tiles if cost[t] > 0]
+    bw = [pre[b[1]] - pre[b[0]] for b in blocks]
+    load = [0.0] * world
+    held = [set() for _ in range(world)]
+    mine = [[] for _ in range(world)]
+    # largest tile first, to the least loaded rank; among (near-)equally loaded ranks the one that already holds
+    # the tile's blocks, so that a rank touches as few blocks as possible
+    total = sum(cost.values())
+    for t in sorted(tiles, key=lambda t: (-cost[t], t)):
+        lo = min(load)
+        cands = [r for r in range(world) if load[r] - lo <= 1e-9 * max(total, 1.0)]
+        r = min(cands, key=lambda r: (sum(bw[b] for b in set(t) - held[r]), r))
+        load[r] += cost[t]
+        held[r] |= set(t)
+        mine[r].append(t)
+    mean = total / world if total > 0 else 1.0
+    imbalance = max(load) / mean if total > 0 else 1.0
+    resident = max((sum(bw[b] for b in h) for h in held), default=0.0) / max(pre[-1], 1.0)
+    return blocks, mine, load, imbalance, resident
+
+
+def plan_exhaustive(sizes: Sequence[int], world: int, rank: int, max_imbalance: float = 1.03) -> ExhaustivePlan:
+    """All pairs i < j over ``len(sizes)`` images on ``world`` ranks.  The block count of the tiling is the one
+    (up to 4 * world blocks) whose cost-balanced tile assignment stays within ``max_imbalance`` while a rank holds
+    the smallest share of the descriptors; if none does, the best balanced one.  Every rank computes the same plan."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    N = len(sizes)
+    best = None
+    for nb in range(1, max(2, 4 * world) + 1):
+        blocks, mine, load, imb, res = _assign_tiles(sizes, world, nb)
+        key = (0, res, imb, nb) if imb <= max_imbalance else (1, imb, res, nb)
+        if best is None or key < best[0]:
+            best = (key, blocks, mine, load, imb, res)
+        if len(blocks) < nb:
+            break
+    _, blocks, mine, load, imb, res = best
+    owners = _balanced_cuts(sizes.astype(np.float64), world)
+    owner = np.zeros(N, dtype=np.int64)
+    for g, (s, e) in enumerate(owners):
+        owner[s:e] = g
+
+    def needed(g):
+        rows = set()
+        for (i, j) in mine[g]:
+            rows.update(range(*blocks[i]))
+            rows.update(range(*blocks[j]))
+        return rows
+
+    need = sorted(needed(rank))
+    recv = [(i, int(owner[i])) for i in need if owner[i] != rank]
+    send = sorted((i, g) for g in range(world) if g != rank for i in needed(g) if owner[i] == rank)
+    pr = []
+    for (i, j) in sorted(mine[rank]):
+        (s1, e1), (s2, e2) = blocks[i], blocks[j]
+        if i == j:
+            pr += [(a, b) for a in range(s1, e1) for b in range(a + 1, e1)]
+        else:
+            pr += [(a, b) for a in range(s1, e1) for b in range(s2, e2)]
+    return ExhaustivePlan(rank, world, owners[rank], blocks, sorted(mine[rank]), need, recv, send,
+                          np.asarray(pr, dtype=np.uint32).reshape(-1, 2), float(load[rank]), float(imb), float(res))
