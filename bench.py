@@ -4,11 +4,20 @@
     python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W # the CPU matcher on the host cores
 
-A "step" is one pass of the hot path over one batch: every image pair of the sequential window
-(BASELINE.json configs[1]: 100 synthetic images x 8192 descriptors, overlap=10, cross_check on -> 855
-pairs per GPU).  With N > 1 (torchrun, one rank per GPU) every rank owns 100 consecutive images of a
-100*N-image sequence (weak scaling) and fetches the overlap-1 = 9 halo images it needs from the next
-rank's HBM over NCCL/NVLink inside the timed step.  Prints ONE JSON line on rank 0.
+Headline ("value", "e2e", "roofline"): a "step" is one pass of the hot path over one batch: every image pair of
+the sequential window of BASELINE.json configs[1] (100 synthetic images x 8192 descriptors, overlap=10,
+cross_check on -> 855 pairs per GPU).  With N > 1 (torchrun, one rank per GPU) every rank owns 100 consecutive
+images of a 100*N-image sequence (weak scaling) and fetches the overlap-1 = 9 halo images it needs from the next
+rank's HBM over NCCL/NVLink inside the timed step.
+
+The same JSON line also carries, measured in the same run at the same N (unless --no-extra):
+  "strong"      BASELINE configs[2]: 1000 x 8192, overlap 20 (18,810 pairs) cut into image windows + halos
+  "ragged"      BASELINE configs[3]: 2000 images of 1k-16k descriptors, overlap 10, cost-balanced windows
+  "exhaustive"  BASELINE configs[4]: 200 x 16384, all 19,900 pairs, 2-D tiling of the pair triangle
+and "parity": a seeded sample of the pairs of the LAST TIMED call of every one of these (every class of halo pair
+included) compared byte for byte with the CPU oracle on every rank; any mismatch makes the run exit non-zero.
+
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -39,6 +48,15 @@ def _env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def host_cores() -> int:
+    """Cores this process may run on (the CPU arm uses all of them, whatever OMP_NUM_THREADS says:
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler(threading.Thread):
@@ -111,13 +129,21 @@ def _physical_gpu_index(local_index: int) -> int:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU matcher (oracle port of COLMAP's MatchSiftFeaturesCPU) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(num_pairs: int, threads: int = 0):
-    """Time ``num_pairs`` pairs of the bench workload (adjacent 8192-descriptor images) on the CPU oracle."""
+_CPU_IMAGES = {}
+
+
+def cpu_sample(num_pairs: int, threads: int):
+    """Time ``num_pairs`` pairs of the bench workload (8192-descriptor images inside one overlap window) on the
+    CPU oracle with ``threads`` OpenMP threads (explicit: OMP_NUM_THREADS is ignored)."""
     from oracle import oracle
     from scanner_colmap_b200 import synth
-    n_img = max(2, min(num_pairs + 1, OVERLAP))
-    imgs = synth.make_images(n_img, N_DESC)
-    pairs = [(k % (n_img - 1), k % (n_img - 1) + 1) for k in range(num_pairs)]
+    n_img = OVERLAP
+    for i in range(n_img):
+        if i not in _CPU_IMAGES:
+            _CPU_IMAGES[i] = synth.make_image(i, N_DESC)
+    imgs = [_CPU_IMAGES[i] for i in range(n_img)]
+    window = [(a, b) for a in range(n_img) for b in range(a + 1, n_img)]       # the pairs of one window
+    pairs = [window[k % len(window)] for k in range(num_pairs)]
     t0 = time.perf_counter()
     res, used = oracle.match_many(imgs, pairs, num_threads=threads)
     dt = time.perf_counter() - t0
@@ -125,27 +151,33 @@ def cpu_sample(num_pairs: int, threads: int = 0):
 
 
 def run_reference(args):
+    """Rank 0 alone times the CPU matcher; the other ranks of a torchrun launch exit 0 without work."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return 0
-    import __graft_entry__ as g
     from oracle import oracle
     oracle.build()
-    cores = oracle.num_procs()
-    total_steps = args.steps + args.warmup
-    sample = max(1, min(cores, int(cores * 16 / max(total_steps, 1))))
-    for _ in range(args.warmup):
-        cpu_sample(sample)
+    cores = host_cores()
+    # every core gets one pair per wave; 2 waves per timed step, 1 per warm-up step.  One 8192 x 8192 pair costs a
+    # core ~2.2 s, so K timed steps take ~4.4 K s: the step COUNT is honoured, the sample per step is what is bounded.
+    _, _, t_wave, _ = cpu_sample(cores, cores)                    # calibration / first warm-up step
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_sample(cores, cores)
+    budget = float(os.environ.get("SMB_REF_BUDGET_S", "150"))
+    waves = 2 if 2 * t_wave * args.steps <= budget else 1
+    sample = waves * cores
     t = 0.0
     for _ in range(args.steps):
-        _, used, dt, _ = cpu_sample(sample)
+        _, used, dt, _ = cpu_sample(sample, cores)
         t += dt
     value = sample * args.steps / t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"each step = {sample} of the workload's 855 pairs (bounded CPU sample)",
+        "config": {"workload": WORKLOAD,
+                   "sample": f"each step = {sample} of the workload's 855 pairs per GPU (bounded CPU sample: "
+                             f"{waves} pair(s) per core), all {cores} host cores busy",
                    "note": "CPU restatement of COLMAP MatchSiftFeaturesCPU (oracle/sift_match_oracle.c, gcc -O3 "
                            "-march=x86-64-v3, OpenMP over pairs); the Eigen/COLMAP/Scanner binary is unbuildable here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
@@ -189,106 +221,174 @@ def int8_gemm_peak(torch, dev):
         return None
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from scanner_colmap_b200 import SiftMatcher, synth, sequential_pairs
+class Ctx:
+    """Per-rank state shared by the headline and the extra configurations."""
 
-    world = _env_int("WORLD_SIZE", 1)
-    rank = _env_int("RANK", 0)
-    local = _env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = _env_int("WORLD_SIZE", 1)
+        self.rank = _env_int("RANK", 0)
+        self.local = _env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from scanner_colmap_b200 import SiftMatcher
+        self.m = SiftMatcher(device=self.local, profile=True)
+        self.stream = torch.cuda.ExternalStream(self.m.stream, device=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.threads = max(1, host_cores() // self.world)     # oracle threads of this rank's parity checks
+        self.parity = {"pairs_checked": 0, "halo_pairs_checked": 0, "ok": True, "mismatches": []}
 
-    # ---- workload: 100 * world images in one sequence; this rank's contiguous anchor window + its halo
-    from scanner_colmap_b200 import sharding
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self):
+        self.flush.fill_(1)
+        self.torch.cuda.synchronize()
+
+    def pool_bytes(self, image_id):
+        """Host copy of what the device pool holds for an image (what the kernels actually read)."""
+        ptr, n = self.m.image_device_ptr(image_id)
+        if n == 0:
+            return np.empty((0, 128), dtype=np.uint8)
+        return self.torch.as_tensor(_DevView(ptr, n * 128), device=self.dev).cpu().numpy().reshape(n, 128).copy()
+
+    def make_exchange(self, plan, row_bytes, halo_ids, halo_ns):
+        """Returns f(): receive this rank's halo / needed rows from their owners' descriptor pools over NCCL (one
+        message per peer, a zero-copy view of the pool when the rows are adjacent there) and adopt them with
+        smb_put_images_device_async.  Nothing in f waits on the host."""
+        torch, m, dev = self.torch, self.m, self.dev
+        from scanner_colmap_b200 import sharding
+        if self.world == 1 or (not plan.recv and not plan.send):
+            return lambda: None
+        per_src = {}
+        for row, src in plan.recv:
+            per_src[src] = per_src.get(src, 0) + row_bytes(row)
+        bufs = {src: torch.empty(nb, dtype=torch.uint8, device=dev) for src, nb in per_src.items()}
+
+        def send_span(rows):
+            spans = [m.image_device_ptr(r) for r in rows]
+            if all(spans[k][0] + spans[k][1] * 128 == spans[k + 1][0] for k in range(len(spans) - 1)):
+                return torch.as_tensor(_DevView(spans[0][0], sum(n for _, n in spans) * 128), device=dev)
+            return torch.cat([torch.as_tensor(_DevView(ptr, n * 128), device=dev) for ptr, n in spans if n])
+
+        def f():
+            cur = torch.cuda.current_stream()
+            m.stream_wait_uploads(cur.cuda_stream)      # rows this rank SENDS may still be crossing PCIe (e2e path)
+            got = sharding.exchange_halo_packed(plan, row_bytes, send_span, lambda src, nb: bufs[src])
+            if halo_ids:
+                m.put_images_device_async(halo_ids, [got[r].data_ptr() for r in halo_ids], halo_ns, cur.cuda_stream)
+        return f
+
+    def check_parity(self, tag, res, pairs, sample, host_image, halo_rows=()):
+        """Compare the matches of pairs[sample] in the completed result `res` with the CPU oracle, byte for byte."""
+        from oracle import oracle
+        if not len(sample):
+            return
+        ids = sorted({int(x) for k in sample for x in pairs[k]})
+        pos = {i: k for k, i in enumerate(ids)}
+        imgs = [host_image(i) for i in ids]
+        want, _ = oracle.match_many(imgs, [(pos[int(pairs[k][0])], pos[int(pairs[k][1])]) for k in sample],
+                                    num_threads=self.threads)
+        halo = set(int(r) for r in halo_rows)
+        for k, w in zip(sample, want):
+            g = res.matches(int(k))
+            self.parity["pairs_checked"] += 1
+            if int(pairs[k][0]) in halo or int(pairs[k][1]) in halo:
+                self.parity["halo_pairs_checked"] += 1
+            if g.shape != w.shape or g.tobytes() != w.tobytes():
+                self.parity["ok"] = False
+                self.parity["mismatches"].append(f"{tag} rank {self.rank} pair {tuple(int(x) for x in pairs[k])}: "
+                                                 f"{len(g)} vs oracle {len(w)}")
+
+
+def sample_pairs(pairs, n_plain, halo_rows, seed):
+    """Seeded sample: `n_plain` pairs without a halo image + one pair per halo image (every class of halo pair)."""
+    rng = np.random.default_rng(seed)
+    halo = set(int(r) for r in halo_rows)
+    is_halo = np.array([int(b) in halo or int(a) in halo for a, b in pairs], dtype=bool) if len(pairs) else np.zeros(0, bool)
+    plain = np.nonzero(~is_halo)[0]
+    out = list(rng.choice(plain, size=min(n_plain, len(plain)), replace=False)) if len(plain) else []
+    for r in sorted(halo):
+        idx = np.nonzero([int(b) == r or int(a) == r for a, b in pairs])[0]
+        if len(idx):
+            out.append(int(rng.choice(idx)))
+    return sorted(set(int(k) for k in out))
+
+
+def run_headline(cx: Ctx, args):
+    torch, dist, m, dev, world, rank = cx.torch, cx.dist, cx.m, cx.dev, cx.world, cx.rank
+    from scanner_colmap_b200 import synth, sharding
     sizes = [N_DESC] * (IMAGES_PER_GPU * world)
     sp = sharding.plan(sizes, OVERLAP, world, rank)
     own_ids = list(range(*sp.own))
     halo_ids = [row for row, _ in sp.recv]
     imgs = [torch.from_numpy(synth.make_image(i, N_DESC)).pin_memory() for i in own_ids]
     imgs_np = [t.numpy() for t in imgs]
+    host = {i: a for i, a in zip(own_ids, imgs_np)}
     pairs = sp.pairs                      # table row == image id here
     h2d = sum(a.nbytes for a in imgs_np)
+    halo_exchange = cx.make_exchange(sp, lambda row: N_DESC * 128, halo_ids, [N_DESC] * len(halo_ids))
 
-    m = SiftMatcher(device=local, profile=True)
-    stream = torch.cuda.ExternalStream(m.stream, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    halo_src = {}                                     # one contiguous receive buffer per owning rank
-    for row, src in sp.recv:
-        halo_src[src] = halo_src.get(src, 0) + N_DESC * 128
-    halo_src = {src: torch.empty(nb, dtype=torch.uint8, device=dev) for src, nb in halo_src.items()}
-
-    def halo_exchange():
-        """Halo rows come straight out of the owning rank's descriptor pool over NCCL, one message per peer
-        (a zero-copy view of the pool when the rows are adjacent there, which they are for whole 256-row images).
-        Nothing here waits on the host: the receives are queued on torch's stream and adopted with
-        smb_put_images_device_async, so the next match call starts on the pairs that need no halo image and only
-        its last sub-batch waits (on the device) for the exchange."""
-        if world == 1:
-            return
-        def send_span(rows):
-            spans = [m.image_device_ptr(r) for r in rows]
-            if all(spans[k][0] + spans[k][1] * 128 == spans[k + 1][0] for k in range(len(spans) - 1)):
-                return torch.as_tensor(_DevView(spans[0][0], sum(n for _, n in spans) * 128), device=dev)
-            return torch.cat([torch.as_tensor(_DevView(ptr, n * 128), device=dev) for ptr, n in spans])
-        got = sharding.exchange_halo_packed(sp, lambda row: N_DESC * 128, send_span, lambda src, nb: halo_src[src])
-        m.put_images_device_async(halo_ids, [got[row].data_ptr() for row in halo_ids], [N_DESC] * len(halo_ids),
-                                  torch.cuda.current_stream().cuda_stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def flush_l2():
-        flush.fill_(1)
-        torch.cuda.synchronize()
+    def host_image(i):                    # halo images: regenerated here, so the NVLink transfer is checked too
+        if i not in host:
+            host[i] = synth.make_image(i, N_DESC)
+        return host[i]
 
     # ---- kernel-resident measurement: descriptors already in HBM when the timed region starts
     m.put_images(own_ids, imgs_np)
     halo_exchange()
     matches_per_step = 0
     for _ in range(args.warmup):
+        halo_exchange()
         matches_per_step = m.match_pairs_count(pairs)
-    sampler = ClockSampler(_physical_gpu_index(local), period=0.01)
+    sampler = ClockSampler(_physical_gpu_index(cx.local), period=0.01)
     sampler.start()
-    barrier()
-    dev_ms, score_ms, launches, score_launches, ops = 0.0, 0.0, 0, 0, 0
+    cx.barrier()
+    acc = {"dev_ms": 0.0, "score_ms": 0.0, "runner_up_ms": 0.0, "decide_ms": 0.0, "launches": 0, "score_launches": 0,
+           "ops": 0, "plan_uploads": 0}
+    last = None
     for _ in range(args.steps):
-        flush_l2()
-        barrier()
+        cx.flush_l2()
+        cx.barrier()
+        if last is not None:
+            last.release()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # the halo (NCCL) is issued on torch's stream, the matcher runs on the library's stream: the first event
         # goes where the step's first device work goes, the second after its last
-        e0.record(torch.cuda.current_stream() if world > 1 else stream)
+        e0.record(torch.cuda.current_stream() if world > 1 else cx.stream)
         halo_exchange()
-        m.match_pairs_count(pairs)
-        e1.record(stream)
+        last = m.match_pairs_result(pairs)          # the call a user makes; results are in pinned host memory
+        e1.record(cx.stream)
         e1.synchronize()
-        step_ms = e0.elapsed_time(e1)
         t = m.timing()
-        dev_ms += step_ms
-        score_ms += t["score_ms"]
-        launches += t["total_launches"]
-        score_launches += t["score_launches"]
-        ops = t["ops"]
-    barrier()
+        acc["dev_ms"] += e0.elapsed_time(e1)
+        for k in ("score_ms", "runner_up_ms", "decide_ms"):
+            acc[k] += t[k]
+        acc["launches"] += t["total_launches"]
+        acc["score_launches"] += t["score_launches"]
+        acc["ops"] += t["ops"]
+        acc["plan_uploads"] += t["plan_uploaded"]
+    cx.barrier()
     clocks = sampler.stop()
+    cx.check_parity("resident", last, pairs, sample_pairs(pairs, 32 - min(len(halo_ids), 9), halo_ids, 1000 + rank),
+                    host_image, halo_ids)
+    last.release()
 
     # ---- end to end through the public API: host (pinned) descriptors in, matches out, every step.
-    # The images are uploaded asynchronously in 3 chunks (a short first one, so matching can start early) and
-    # ONE match_pairs call follows: the library takes the pairs in the order their images land, one sub-batch
-    # per upload ticket, each waiting on the device for its own ticket only -- so the copy of chunk k+1 overlaps
-    # the matching of chunk k without any host round trip in between.
+    # The images are uploaded asynchronously in 3-4 chunks (a short first one, so matching can start early) and ONE
+    # match call follows: the library takes the pairs in the order their images land, one sub-batch per upload
+    # ticket, each waiting on the device for its own ticket only -- so the copy of chunk k+1 overlaps the matching of
+    # chunk k without any host round trip in between.  With N > 1 the halo this rank SENDS is its first overlap-1
+    # images: the NCCL send is ordered behind their upload on the device (smb_stream_wait_uploads), not on the host.
     n_own = len(own_ids)
-    # chunk sizes grow so that the upload of chunk k+1 (~55 GB/s) hides under the matching of chunk k: 16 / 24 / 60
-    # images of 100 measured best (tools/e2e_chunks.py)
-    # (with 8 ranks uploading at once the host link is slower and a shorter first chunk + four chunks measured better)
     if world == 1:
         first = min(n_own, OVERLAP + 6)
         bounds = sorted(set([0, first, max(first, (2 * n_own) // 5), n_own]))
@@ -302,32 +402,148 @@ def run_ours(args):
         for c in range(n_chunks):
             lo, hi = bounds[c], bounds[c + 1]
             m.put_images_async(own_ids[lo:hi], imgs_np[lo:hi])
-            if c == 0 and world > 1:
-                m.synchronize()       # the halo this rank SENDS is its first overlap-1 images
+            if c == 0:
                 halo_exchange()
-        return m.match_pairs_count(pairs)
+        return m.match_pairs_result(pairs)
 
     for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    e2e_ms = 0.0
+        e2e_step().release()
+    cx.barrier()
+    e2e_ms, last, total = 0.0, None, 0
     for _ in range(args.steps):
-        flush_l2()
-        barrier()
+        cx.flush_l2()
+        cx.barrier()
+        if last is not None:
+            last.release()
         t0 = time.perf_counter()
-        total = e2e_step()
-        m.synchronize()
+        last = e2e_step()
+        total = last.total
         e2e_ms += (time.perf_counter() - t0) * 1e3
-    barrier()
-    d2h = int(total) * 8 + len(pairs) * 8 + 16
+    cx.barrier()
+    cx.check_parity("e2e", last, pairs, sample_pairs(pairs, 16 - min(len(halo_ids), 9) if world > 1 else 16,
+                                                      halo_ids, 2000 + rank), host_image, halo_ids)
+    last.release()
+    d2h = int(total) * 8 + len(pairs) * 8 + 48
 
-    times = torch.tensor([dev_ms, e2e_ms, score_ms], dtype=torch.float64, device=dev)
+    red_max = torch.tensor([acc["dev_ms"], e2e_ms, acc["score_ms"]], dtype=torch.float64, device=dev)
+    rate = acc["ops"] / (acc["score_ms"] * 1e-3) / 1e12 if acc["score_ms"] > 0 else 0.0
+    red_min = torch.tensor([rate], dtype=torch.float64, device=dev)
     npairs = torch.tensor([float(len(pairs))], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(red_min, op=dist.ReduceOp.MIN)
         dist.all_reduce(npairs, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, score_ms_max = [float(x) for x in times.tolist()]
-    total_pairs = float(npairs.item())
+    dev_ms, e2e_ms_max, score_ms_max = [float(x) for x in red_max.tolist()]
+    return {"dev_ms": dev_ms, "e2e_ms": e2e_ms_max, "score_ms_max": score_ms_max, "rate_min": float(red_min.item()),
+            "rate_rank0": rate, "total_pairs": float(npairs.item()), "acc": acc, "clocks": clocks, "h2d": h2d,
+            "d2h": d2h, "matches_per_step": matches_per_step, "pairs_rank0": len(pairs)}
+
+
+def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=6):
+    """One more BASELINE configuration at this run's N: descriptors generated on the GPU and resident in HBM, the
+    halo / needed-row exchange over NCCL inside the timed step, one match call per step, L2 flushed between steps."""
+    torch, dist, m, dev, world, rank = cx.torch, cx.dist, cx.m, cx.dev, cx.world, cx.rank
+    from scanner_colmap_b200 import synth, sharding
+    m.clear_images()
+    plan = sharding.plan_exhaustive(sizes, world, rank) if exhaustive else sharding.plan(sizes, overlap, world, rank)
+    own_ids = list(range(*plan.own))
+    halo_ids = [row for row, _ in plan.recv]
+    for lo in range(0, len(own_ids), 64):                      # generate + adopt in slabs (bounded scratch)
+        ids = own_ids[lo:lo + 64]
+        ts = [synth.make_image_torch(i, sizes[i], dev) for i in ids]
+        torch.cuda.synchronize()
+        m.put_images_device(ids, [t.data_ptr() for t in ts], [int(sizes[i]) for i in ids])
+        del ts
+    pairs = plan.pairs
+    exchange = cx.make_exchange(plan, lambda row: int(sizes[row]) * 128, halo_ids, [int(sizes[r]) for r in halo_ids])
+    exchange()
+    m.match_pairs_count(pairs)                                  # warm-up (allocations, pool growth)
+    cx.barrier()
+    ms, score_ms, ops, launches, last = 0.0, 0.0, 0, 0, None
+    for _ in range(steps):
+        cx.flush_l2()
+        cx.barrier()
+        if last is not None:
+            last.release()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream() if world > 1 else cx.stream)
+        exchange()
+        last = m.match_pairs_result(pairs)
+        e1.record(cx.stream)
+        e1.synchronize()
+        t = m.timing()
+        ms += e0.elapsed_time(e1)
+        score_ms += t["score_ms"]
+        ops += t["ops"]
+        launches += t["score_launches"]
+    cx.barrier()
+    # parity sample; halo rows are regenerated on this GPU, which also checks the bytes NVLink delivered
+    def host_image(i):
+        got = cx.pool_bytes(i)
+        if i in halo_set:
+            exp = synth.make_image_torch(i, sizes[i], dev).cpu().numpy()
+            if exp.shape != got.shape or exp.tobytes() != got.tobytes():
+                cx.parity["ok"] = False
+                cx.parity["mismatches"].append(f"{name} rank {rank}: halo image {i} differs from its owner's bytes")
+        return got
+    halo_set = set(halo_ids)
+    # (a 16384 x 16384 pair costs a host core ~9 s: the exhaustive record checks one plain and one received pair)
+    n_halo = 1 if exhaustive else 3
+    smp = sample_pairs(pairs, n_check, halo_ids[:: max(1, len(halo_ids) // n_halo)][:n_halo] if halo_ids else [], 3000 + rank)
+    cx.check_parity(name, last, pairs, smp, host_image, halo_ids)
+    total_matches = last.total if last is not None else 0
+    last.release()
+    per_rank = torch.tensor([ms / steps, score_ms / steps, float(len(pairs)), float(ops / steps)], dtype=torch.float64, device=dev)
+    allr = [per_rank.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, per_rank)
+    allr = torch.stack(allr).cpu().numpy()
+    step_ms = allr[:, 0]
+    tot_pairs, tot_ops = float(allr[:, 2].sum()), float(allr[:, 3].sum())
+    m.clear_images()
+    rec = {
+        "pairs": int(tot_pairs), "ms_per_step": float(step_ms.max()), "pairs_per_s": tot_pairs / (step_ms.max() * 1e-3),
+        "top_per_s": tot_ops / (step_ms.max() * 1e-3) / 1e12, "steps": steps,
+        "rank_step_ms_max_over_mean": float(step_ms.max() / step_ms.mean()),
+        "rank_score_ms": [round(float(x), 3) for x in allr[:, 1]],
+        "score_launches_per_step_rank0": launches // max(steps, 1), "matches_rank0": int(total_matches),
+        "halo_bytes_in_rank0": int(sum(int(sizes[r]) * 128 for r in halo_ids)),
+    }
+    if exhaustive:
+        rec.update({"distribution": "2-D tiling of the pair triangle over image blocks (sharding.plan_exhaustive); each rank "
+                                    "receives only the blocks its tiles touch from their owners' pools (NCCL send/recv)",
+                    "blocks": len(plan.blocks), "plan_cost_imbalance": plan.imbalance,
+                    "resident_fraction_max": plan.resident_fraction})
+    return rec
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    torch, dist, m, world, rank = cx.torch, cx.dist, cx.m, cx.world, cx.rank
+    from scanner_colmap_b200 import synth
+    hd = run_headline(cx, args)
+    extras = {}
+    if not args.no_extra:
+        extras["strong"] = run_extra(cx, "strong", [N_DESC] * 1000, 20, n_check=6)
+        extras["strong"]["workload"] = "BASELINE.json configs[2]: 1000 images x 8192, sequential overlap=20, image windows + halo"
+        rs = synth.ragged_sizes(2000).tolist()
+        extras["ragged"] = run_extra(cx, "ragged", rs, 10, n_check=8)
+        extras["ragged"]["workload"] = ("BASELINE.json configs[3]: 2000 images with 1k-16k descriptors (log-uniform, seed 1234), "
+                                        "overlap=10, cost-balanced windows")
+        extras["exhaustive"] = run_extra(cx, "exhaustive", [16384] * 200, 0, exhaustive=True, n_check=1)
+        extras["exhaustive"]["workload"] = "BASELINE.json configs[4]: exhaustive matching, 200 images x 16384 (19,900 pairs)"
+
+    # parity verdict of every rank
+    par = torch.tensor([cx.parity["pairs_checked"], cx.parity["halo_pairs_checked"], 0 if cx.parity["ok"] else 1],
+                       dtype=torch.float64, device=cx.dev)
+    if world > 1:
+        dist.all_reduce(par, op=dist.ReduceOp.SUM)
+    parity = {"pairs_checked": int(par[0].item()), "halo_pairs_checked": int(par[1].item()), "ok": par[2].item() == 0,
+              "how": "after timing, every rank compares a seeded sample of the pairs of its LAST TIMED call (resident, "
+                     "end-to-end and each extra configuration; one pair per halo image included) byte for byte with "
+                     "oracle.match_many on the same descriptors"}
+    if cx.parity["mismatches"]:
+        print("PARITY MISMATCH: " + "; ".join(cx.parity["mismatches"][:8]), file=sys.stderr, flush=True)
 
     if rank == 0:
         peaks = {}
@@ -335,67 +551,78 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        bf16_sus = peaks.get("bf16_tflops_sustained")
-        bf16_burst = peaks.get("bf16_tflops")
-        if bf16_sus:
-            peak, peak_src = 2.0 * bf16_sus, ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kind::i8 issues at twice the "
-                                              "kind::f16 rate; kernel timed inside a long step)")
+        bf16_burst, bf16_sus = peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")
+        if bf16_burst:
+            peak, peak_src = 2.0 * bf16_burst, ("2 x bf16_tflops (burst) of MEASURED_PEAKS.json, of measured: kind::i8 issues at "
+                                                "exactly twice the kind::f16 MAC rate and the kernel is timed alone, at full clock")
         else:
-            peak, peak_src = 2.0 * 1400.0, "2 x 1.4 PFLOP/s sustained bf16 fallback of B200_PROFILING.md"
-        launch_ms = score_ms / max(score_launches, 1)
-        achieved = ops / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+            peak, peak_src = 2.0 * 1590.0, "2 x 1.59 PFLOP/s burst bf16, the fallback of B200_PROFILING.md (of fallback)"
+        acc = hd["acc"]
+        launches_per_step = max(acc["score_launches"] // max(args.steps, 1), 1)
+        launch_ms = acc["score_ms"] / max(acc["score_launches"], 1)
+        achieved = hd["rate_min"]
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
-        int8_meas = int8_gemm_peak(torch, dev)
+        int8_meas = int8_gemm_peak(torch, cx.dev)
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle
             oracle.build()
-            cores = oracle.num_procs()
-            sample = 4 * cores                     # ~10 s of CPU work on the 16-core box
-            v, used, dt, _ = cpu_sample(sample)
+            cores = host_cores()
+            sample = 4 * cores                     # ~10 s of CPU work
+            v, used, dt, _ = cpu_sample(sample, cores)
             cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": f"{sample} of the workload's 8192x8192 pairs, {dt:.1f} s on {used} threads "
                              f"(oracle/sift_match_oracle.c: COLMAP MatchSiftFeaturesCPU restated, gcc -O3 x86-64-v3)"}
 
+        steps = args.steps
         line = {
-            "metric": METRIC, "value": total_pairs * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "metric": METRIC, "value": hd["total_pairs"] * steps / (hd["dev_ms"] * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": hd["dev_ms"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD,
-                "pairs_per_step": int(total_pairs), "matches_per_step_rank0": int(matches_per_step),
+                "pairs_per_step": int(hd["total_pairs"]), "matches_per_step_rank0": int(hd["matches_per_step"]),
                 "l2": "flushed between timed steps (256 MiB write)",
-                "timing": "CUDA events on the library stream around the whole smb_match_pairs call (plan upload, kernels, "
-                          "result copy); max over ranks",
+                "timing": "CUDA events around the whole step on the device: halo exchange (N > 1) + one match call (plan, "
+                          "accumulator reset, score, runner-up, decide writing the matches into pinned host memory); "
+                          "max over ranks",
                 "multi_gpu": "contiguous, cost-balanced image windows (sharding.plan); the overlap-1 halo images are received "
                              "from the next rank's descriptor pool over NCCL send/recv inside every timed step; no "
                              "other collective" if world > 1 else "single GPU",
             },
-            "clocks": clocks,
-            "e2e": {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "clocks": hd["clocks"],
+            "e2e": {"value": hd["total_pairs"] * steps / (hd["e2e_ms"] * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(hd["h2d"]), "d2h_bytes_per_step": int(hd["d2h"]),
                     "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 3-4 chunks) + "
-                            "one match_pairs call (sub-batches wait on the device for their own upload; matches land "
-                            "in pinned host memory)"},
-            "gpu_launches": int(launches),
+                            "halo exchange (N > 1, ordered behind the uploads on the device) + one match call whose "
+                            "sub-batches wait on the device for their own upload; matches land in pinned host memory"},
+            "gpu_launches": int(acc["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "score_tcgen05_kernel",
-                         "algorithmic_ops_per_launch": int(ops), "launch_ms": launch_ms,
+                         "algorithmic_ops_per_launch": int(acc["ops"] // max(acc["score_launches"], 1)),
+                         "launch_ms": launch_ms, "launches_per_step": launches_per_step,
+                         "how": "sum of algorithmic ops (2*n1*n2*128 per pair) / sum of the score kernel's own CUDA-event time "
+                                "over the timed steps, per rank; the MINIMUM over ranks is reported",
                          "peak_source": peak_src, "frac_of_spec_4500": achieved / INT8_SPEC_TOPS,
-                         "int8_gemm_measured_here": int8_meas, "bf16_burst": bf16_burst},
+                         "int8_gemm_measured_here": int8_meas, "bf16_sustained": bf16_sus,
+                         "other_kernels_ms_per_step": {"runner_up_kernel": acc["runner_up_ms"] / steps,
+                                                       "decide_kernel": acc["decide_ms"] / steps},
+                         "plan_uploads_in_timed_steps": int(acc["plan_uploads"])},
             "cpu_baseline": cpu,
+            "parity": parity,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     m.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if parity["ok"] else 3
 
 
 def main():
@@ -406,6 +633,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong / ragged / exhaustive records")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMB_ABI_VERSION 1
+#define SMB_ABI_VERSION 2
 #define SMB_DESC_DIM 128 /* SIFT descriptor bytes; FeatureDescriptors cols, io.cc:181-194 */
 
 enum {
@@ -40,10 +40,12 @@ enum {
   SMB_ECAPACITY = -5  /* caller buffer too small */
 };
 
-/* Which device kernel computes the dot-product tiles. */
+/* Which device kernel computes the dot-product tiles.  The product library (libsmb.so) contains exactly one
+ * engine; SMB_ENGINE_DP4A exists only in the test build (libsmb_test.so, compiled with -DSMB_TEST_ENGINES) where
+ * it cross-checks the tensor-core path on CUDA cores.  libsmb.so rejects it with SMB_EINVAL. */
 enum {
-  SMB_ENGINE_TCGEN05 = 0, /* production: TMA + tcgen05.mma kind::i8 + TMEM (default) */
-  SMB_ENGINE_DP4A = 1     /* test-only device cross-check: CUDA-core __dp4a tiles, same epilogue contract */
+  SMB_ENGINE_TCGEN05 = 0, /* TMA + tcgen05.mma kind::i8 + TMEM */
+  SMB_ENGINE_DP4A = 1     /* test builds only */
 };
 
 /* Mirrors the fields of colmap::SiftMatchingOptions that MatchSiftFeaturesCPU reads,
@@ -70,14 +72,17 @@ typedef struct smb_match {
 typedef struct smb_handle smb_handle;
 typedef struct smb_result smb_result;
 
-/* Device timings of the most recent smb_match_pairs call (milliseconds, CUDA events on the
- * handle's stream; valid only when options.profile != 0). */
+/* Device timings of the most recent completed match call (milliseconds, CUDA events on the handle's stream; the
+ * *_ms fields are valid only when options.profile != 0). */
 typedef struct smb_timing {
-  float total_ms;       /* first upload to last device->host copy */
-  float score_ms;       /* the score (+ runner-up) kernels only, summed over the call's sub-batches */
-  float decide_ms;      /* reserved (0): the decide kernels run on a second stream under the next sub-batch's scoring */
+  float total_ms;       /* first kernel of the call to the last one (results are in host memory when it ends) */
+  float score_ms;       /* score_tcgen05_kernel only, summed over the call's sub-batches */
+  float runner_up_ms;   /* runner_up_kernel, summed */
+  float decide_ms;      /* decide_kernel (writes the matches straight into pinned host memory), summed */
   uint32_t score_launches;
   uint32_t total_launches; /* every kernel of this library launched by the call */
+  uint32_t sub_batches;
+  uint32_t plan_uploaded;  /* 0: the device-side plan of the previous call was reused (same pairs, same pool rows) */
   uint64_t candidates;  /* score-matrix entries that survived the integer pre-filter */
   uint64_t ops;         /* 2 * sum(n1 * n2) * 128 over the call's pairs */
 } smb_timing;
@@ -133,9 +138,15 @@ int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** de
  * sequential_matching.cc:139-181.  Result i holds exactly what MatchSiftFeaturesCPU would have
  * written to featureMatches for pair i: (idx1, idx2) in ascending idx1. */
 int smb_match_pairs(smb_handle* h, const uint32_t* pairs /* [npairs][2] */, size_t npairs, smb_result** out);
+/* The same call in two halves, so the caller (the op: verification and serialisation of the previous packet) can
+ * work while the GPU matches: _begin queues every kernel and returns; smb_result_wait blocks until the matches
+ * are in host memory.  At most one call may be in flight per handle; descriptor uploads may be queued meanwhile
+ * (smb_put_images_async), evictions take effect for calls begun afterwards. */
+int smb_match_pairs_begin(smb_handle* h, const uint32_t* pairs /* [npairs][2] */, size_t npairs, smb_result** out);
+int smb_result_wait(smb_handle* h, smb_result* r);
 
 size_t smb_result_num_pairs(const smb_result* r);
-/* Matches of pair i; pointer is into pinned host memory owned by the result. */
+/* Matches of pair i; pointer is into pinned host memory owned by the result (the device wrote it directly). */
 const smb_match* smb_result_matches(const smb_result* r, size_t i, size_t* count);
 size_t smb_result_total_matches(const smb_result* r);
 void smb_result_release(smb_handle* h, smb_result* r);
@@ -147,12 +158,21 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
 
 int smb_get_timing(const smb_handle* h, smb_timing* t);
 
+/* Page-locked host memory for callers that do not link the CUDA runtime themselves (the op stages Scanner's
+ * pageable descriptor rows through such a buffer so that smb_put_images_async really is asynchronous). */
+int smb_alloc_pinned(size_t bytes, void** out);
+void smb_free_pinned(void* p);
+
 /* Integer pre-filter derived from the options and the host libm acosf table: score entries
  * below *min_score cannot change any accept/reject decision ("Filter"). */
 int smb_get_filter(const smb_handle* h, int32_t* min_score, int32_t* min_best);
 
 /* CUDA stream the handle launches on (cudaStream_t as void*), for external event timing. */
 void* smb_stream(const smb_handle* h);
+/* Make `stream` (a cudaStream_t of the same device) wait, on the device, for every upload queued so far by the
+ * smb_put_images*_async calls: lets a peer copy / NCCL send read freshly uploaded pool rows (the halo this GPU
+ * provides to its neighbour) without any host synchronisation. */
+int smb_stream_wait_uploads(smb_handle* h, void* stream);
 int smb_synchronize(smb_handle* h);
 
 #ifdef __cplusplus

@@ -112,57 +112,11 @@ constexpr int kBBytes = kTileCols * kDim;      // 32 KiB (two 128-row boxes)
 #ifndef SMB_IDLE_NS
 #define SMB_IDLE_NS 200
 #endif
-// Epilogue organisation.  SMB_EPI_ALT=1 (default): 16 epilogue warps in two groups of 8; group g owns TMEM
-// accumulator buffer g, i.e. every other tile, so a warp has two tile periods (2 x 512 clk of tensor work) for
-// its serial chain barrier wake -> tcgen05.ld -> max trees -> (rare) survivor posting, and the two groups
-// de-phase on their own: one reads TMEM while the other reduces.  Each warp covers 32 rows x 128 columns of its
-// tile in two passes of two 32-column runs (64 registers live).
-// SMB_EPI_ALT=0: the round-1 layout, SMB_EPI_WARPS (8 or 16) warps that ALL work on EVERY tile.
-#ifndef SMB_EPI_ALT
-#define SMB_EPI_ALT 1
-#endif
-#if SMB_EPI_ALT
-#undef SMB_EPI_WARPS
-#define SMB_EPI_WARPS 16
-#endif
 #ifndef SMB_EPI_WARPS
 #define SMB_EPI_WARPS 8
 #endif
-// SMB_HALF_COMMIT=1 (round-1 layout only): every 128 x 256 tile is issued as two N = 128 halves, each with its own
-// tcgen05.commit, t_full and t_empty barrier.  The epilogue warp owning columns 0-127 and its SMSP sibling owning
-// columns 128-255 then wake ~300 clk apart instead of in lock-step: one reads TMEM while the other runs its max
-// trees (the ALU pipe they share is no longer contended), and each half of the buffer goes back to the MMA
-// warp as soon as its own warp-quartet has read it.
-#ifndef SMB_HALF_COMMIT
-#define SMB_HALF_COMMIT 0
-#endif
-constexpr bool kHalfCommit = SMB_HALF_COMMIT != 0;
-static_assert(!(SMB_HALF_COMMIT && SMB_EPI_ALT), "half commits are implemented for the all-warps-on-every-tile layout");
-// SMB_EPI_DIRECT=1 (round-1 layout): an epilogue warp whose tile holds a score >= min_score handles the survivors
-// itself, straight from its registers: the hit lanes scan their hit runs, raise the best keys with RED.MAX and
-// append to the survivor log (per-lane chunks) -- global fire-and-forget traffic only.  No mailbox, no insert
-// warps, nothing extra through the shared-memory port the MMA operand reads saturate (a mailbox post cost the
-// posting warp ~700 clk on 21 % of its tiles).
-#ifndef SMB_EPI_DIRECT
-#define SMB_EPI_DIRECT 0
-#endif
-// SMB_SCOUT=1 (needs SMB_EPI_DIRECT): warps 2 and 3 become barrier proxies, one per TMEM buffer.  An mbarrier
-// operation costs the issuing warp 150-200 clk even when the barrier is already complete; the proxy pays that
-// (long before the epilogue needs the tile) and hands over through a hardware named barrier, and it collects the
-// eight epilogue warps' "buffer read" arrivals the same way before it arrives on t_empty for them.
-#ifndef SMB_SCOUT
-#define SMB_SCOUT 0
-#endif
-constexpr bool kDirect = SMB_EPI_DIRECT != 0;
-constexpr bool kScout = SMB_SCOUT != 0;
-static_assert(!kScout || kDirect, "the scouts take over the insert warps, which only the direct epilogue frees");
-static_assert(!(kDirect && SMB_EPI_ALT), "direct survivor handling is implemented for the all-warps-on-every-tile layout");
-static_assert(!(kScout && SMB_HALF_COMMIT), "scouts proxy whole buffers");
-constexpr bool kEpiAlt = SMB_EPI_ALT != 0;
-constexpr int kEpiWarps = SMB_EPI_WARPS;       // total epilogue warps
-constexpr int kEpiGroups = kEpiAlt ? 2 : 1;    // groups that alternate tiles
-constexpr int kEpiGroupWarps = kEpiWarps / kEpiGroups;   // warps that must release one TMEM buffer
-constexpr int kEpiCols = kTileCols / (kEpiGroupWarps / 4);  // accumulator columns per warp and tile
+constexpr int kEpiWarps = SMB_EPI_WARPS;       // 2 or 4 per TMEM lane quarter, each a column slice of the tile
+constexpr int kEpiCols = kTileCols / (kEpiWarps / 4);  // accumulator columns per warp and tile
 constexpr int kInsertWarps = 2;                // warps 2 and 3
 constexpr int kInsertWarp0 = 2;
 constexpr int kScoreWarps = 4 + kEpiWarps;     // 0 TMA, 1 MMA, 2-3 insert, 4.. epilogue
@@ -171,7 +125,6 @@ constexpr int kRunCols = 32;                   // accumulator columns per thread
 constexpr int kRunsPerWarp = kEpiCols / kRunCols;  // 2 or 4, all in flight at once
 constexpr int kMailSlots = 128 / kEpiWarps;    // per epilogue warp: ring of survivor runs
 static_assert(kRunsPerWarp == 4 || kRunsPerWarp == 2, "epilogue code is written for two or four 32-column runs per warp");
-static_assert(!kEpiAlt || kRunsPerWarp == 4, "alternating groups: 8 warps per tile, 128 columns each");
 
 // A 32-column run of one accumulator row that holds at least one score >= min_score, copied out of the
 // epilogue thread's registers: the exact scores themselves, no recomputation.
@@ -186,7 +139,7 @@ static_assert(sizeof(HitRun) == 144, "HitRun layout");
 struct ScoreShared {
   uint64_t a_full[kAStages], a_empty[kAStages];
   uint64_t b_full[kStages], b_empty[kStages];
-  uint64_t t_full[4], t_empty[4];  // [buffer] or, with half commits, [2 * buffer + column half]
+  uint64_t t_full[2], t_empty[2];
   uint32_t mail_head[kEpiWarps];  // runs posted by epilogue warp e (monotonic)
   uint32_t mail_tail[kEpiWarps];  // runs consumed by its insert warp (monotonic)
   uint32_t epi_done;              // epilogue warps that have finished
@@ -219,11 +172,6 @@ __device__ __forceinline__ uint32_t tr_clock() {
   return c;
 }
 #endif
-__device__ __forceinline__ uint32_t read_clock_ordered() {
-  uint32_t c;
-  asm volatile("mov.u32 %0, %%clock;" : "=r"(c)::"memory");
-  return c;
-}
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
   uint32_t v;
@@ -236,6 +184,12 @@ __device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
   return v;
+}
+// Release store (CTA scope) of a shared-memory word: everything this thread -- and, through a preceding
+// __syncwarp, every lane of its warp -- wrote before it is visible to a thread that then reads the word with
+// ld.acquire.cta.  Publishes the mailbox head (SASS: MEMBAR.ALL.CTA + STS on the one publishing lane).
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -327,7 +281,11 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
         }
         count += surv;
       } while (tail[k] != head);
-      __syncwarp();  // every lane has read the entries before they may be reused
+      // Every lane has consumed what it loaded from the entries (the ballot and the atomics above use the loaded
+      // values, and a warp issues in order), so the loads have completed before the tail store below is issued:
+      // the producer cannot overwrite a slot that is still being read.  A release here instead would wait for
+      // this warp's outstanding global atomics (~2500 clk per pass, measured) -- hence the plain store.
+      __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh->mail_tail[e]) = tail[k];
     }
     if (got) {
@@ -363,51 +321,6 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
 #endif
 }
 
-// ---- direct survivor handling (SMB_EPI_DIRECT): per-lane log chunks
-constexpr uint32_t kLaneChunk = 32;
-struct LaneLog {
-  unsigned long long pos;  // next free entry of this lane's current chunk
-  uint32_t left;           // free entries left in it
-  uint32_t cnt;            // survivors this lane has handled (profiling)
-};
-
-__device__ __forceinline__ void emit_survivor(TopTwo* __restrict__ acc, const SurvivorLog& slog, LaneLog& ll, uint32_t rs,
-                                              uint32_t cs, uint32_t sc) {
-  if (slog.entries) {
-    atomicMax(&acc[rs].k1, make_key(sc, cs));  // results unused: RED, nothing to wait for
-    atomicMax(&acc[cs].k1, make_key(sc, rs));
-    if (ll.left == 0) {  // one returning atomic per kLaneChunk survivors of this lane
-      ll.pos = atomicAdd(slog.count, (unsigned long long)kLaneChunk);
-      ll.left = kLaneChunk;
-    }
-    if (ll.pos < slog.capacity) slog.entries[ll.pos] = make_uint4(rs, cs, sc, 0u);
-    ++ll.pos;
-    --ll.left;
-  } else {
-    top2_insert2(acc, rs, cs, sc);
-  }
-  ++ll.cnt;
-}
-
-// One 32-column run of one row, still in this thread's registers: every score >= min_score is a survivor of its
-// row and its column.  (Registers cannot be indexed dynamically: a bit mask of the survivors is built with 32
-// compares, then each survivor's score is picked by a 32-way select -- a few hundred instructions, but only
-// for a run that holds a survivor.)
-__device__ __forceinline__ void emit_run(TopTwo* __restrict__ acc, const SurvivorLog& slog, LaneLog& ll, const uint32_t (&v)[32],
-                                         int min_score, uint32_t rs, uint32_t cs0) {
-  uint32_t mask = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) mask |= ((int)v[j] >= min_score ? 1u : 0u) << j;
-  while (mask) {
-    const int j = __ffs(mask) - 1;
-    mask &= mask - 1;
-    uint32_t sc = 0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) sc = (j == k) ? v[k] : sc;
-    emit_survivor(acc, slog, ll, rs, cs0 + j, sc);
-  }
-}
-
 // Second stage of the logged insertion: every survivor that is not the final best of its row (column)
 // competes for that row's (column's) runner-up key.  Keys are distinct, so "not the best" == "key != k1".
 __global__ void __launch_bounds__(256)
@@ -426,176 +339,6 @@ runner_up_kernel(const uint4* __restrict__ entries, const unsigned long long* __
     if (acc[e.x].k1 != kr) atomicMax(&acc[e.x].k2, kr);
     if (acc[e.y].k1 != kc) atomicMax(&acc[e.y].k2, kc);
   }
-}
-
-
-// Release store (CTA scope) of a shared-memory word: everything this thread -- and, through a preceding
-// __syncwarp, every lane of its warp -- wrote before it is visible to a thread that reads the word with
-// ld.acquire.cta.  Publishes the mailbox head.
-__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
-}
-// Warp ballot as a volatile asm: volatile asm statements keep their program order, so the max tree feeding
-// the predicate cannot sink below the tcgen05.ld / wait that follows it (the software pipeline of the
-// alternating epilogue relies on that order).
-__device__ __forceinline__ uint32_t ballot_ordered(bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
-      "}\n"
-      : "=r"(r)
-      : "r"((uint32_t)pred)
-      : "memory");
-  return r;
-}
-
-// max over two 32-column runs at once.  The first tree level mixes elements of BOTH runs, so no instruction of
-// the tree can issue before both tcgen05.ld have landed -- which is what keeps the two loads in flight together:
-// left alone, ptxas (a register-pressure-driven scheduler) reduces run a first, parks the temporaries in run
-// b's registers and thereby serialises "load a, reduce a, load b, reduce b" (seen in the SASS).
-__device__ __forceinline__ int max_tree64_mixed(const uint32_t (&a)[32], const uint32_t (&b)[32]) {
-  int l1[22];
-#pragma unroll
-  for (int i = 0; i < 21; ++i) {
-    const int k = 3 * i;  // interleaved sequence x[2j] = a[j], x[2j+1] = b[j]
-    const int x0 = (int)((k & 1) ? b[k >> 1] : a[k >> 1]);
-    const int x1 = (int)(((k + 1) & 1) ? b[(k + 1) >> 1] : a[(k + 1) >> 1]);
-    const int x2 = (int)(((k + 2) & 1) ? b[(k + 2) >> 1] : a[(k + 2) >> 1]);
-    l1[i] = __vimax3_s32(x0, x1, x2);
-  }
-  l1[21] = (int)b[31];
-  int l2[8];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) l2[i] = __vimax3_s32(l1[3 * i], l1[3 * i + 1], l1[3 * i + 2]);
-  l2[7] = l1[21];
-  const int p = __vimax3_s32(l2[0], l2[1], l2[2]);
-  const int q = __vimax3_s32(l2[3], l2[4], l2[5]);
-  return max(__vimax3_s32(p, q, l2[6]), l2[7]);
-}
-
-// Copy the 32-column run `v` of every lane whose bit is set in `lanes` into epilogue warp e's mailbox (one slot
-// per lane), with back-pressure on the consumer's tail.  The new head is NOT published here (see publish_mail).
-__device__ __forceinline__ void stage_runs(ScoreShared* sh, uint32_t e, uint32_t lane, uint32_t lanes, const uint32_t (&v)[32],
-                                           uint32_t row_slot, uint32_t col_slot0, uint32_t& mail_head, uint32_t& mail_tail_seen) {
-  while (lanes) {
-    const int src = __ffs(lanes) - 1;
-    lanes &= lanes - 1;
-    if (mail_head + 1 - mail_tail_seen > (uint32_t)kMailSlots) {  // ring (seems) full: back-pressure
-      __syncwarp();  // publish what has been written so far, or the consumer could never make room
-      if (lane == 0) st_release_shared(&sh->mail_head[e], mail_head);
-      uint32_t spins = 0;
-      do {
-        mail_tail_seen = ld_volatile_shared(&sh->mail_tail[e]);
-        if (++spins > (1u << 28)) __trap();
-      } while (mail_head + 1 - mail_tail_seen > (uint32_t)kMailSlots);
-    }
-    if (lane == (uint32_t)src) store_run(sh, e, mail_head, v, row_slot, col_slot0);
-    ++mail_head;
-  }
-}
-// Release-publish the mailbox head: __syncwarp orders every lane's payload stores before lane 0's
-// st.release.cta, which pairs with the insert warp's ld.acquire.cta of the same word.
-__device__ __forceinline__ void publish_mail(ScoreShared* sh, uint32_t e, uint32_t lane, uint32_t mail_head) {
-  __syncwarp();
-  if (lane == 0) st_release_shared(&sh->mail_head[e], mail_head);
-}
-
-// Two adjacent 32-column runs: one mixed max tree and one ballot; only if some lane holds a score >= min_score
-// (rare) are the runs told apart and the hit runs copied, exact scores and all, from the registers to the mailbox.
-__device__ __forceinline__ void scan_pass(ScoreShared* sh, uint32_t e, uint32_t lane, const uint32_t (&a)[32], const uint32_t (&b)[32],
-                                          int min_score, uint32_t row_slot, uint32_t col_slot0, uint32_t& mail_head,
-                                          uint32_t& mail_tail_seen, uint32_t dbg) {
-  const uint32_t any = ballot_ordered(max_tree64_mixed(a, b) >= min_score);
-  if (any && !(dbg & 4)) {
-    const uint32_t la = __ballot_sync(0xffffffffu, max_tree32(a) >= min_score);
-    const uint32_t lb = __ballot_sync(0xffffffffu, max_tree32(b) >= min_score);
-    stage_runs(sh, e, lane, la, a, row_slot, col_slot0, mail_head, mail_tail_seen);
-    stage_runs(sh, e, lane, lb, b, row_slot, col_slot0 + kRunCols, mail_head, mail_tail_seen);
-  }
-}
-
-// Filter epilogue, alternating groups (SMB_EPI_ALT): warp e of group g = e / 8 handles every tile whose global
-// sequence number (the MMA warp's TMEM ping-pong) has parity g.  Per tile: columns 0-63 of the warp's slice are
-// loaded and reduced, then columns 64-127 are loaded into the same registers, the TMEM buffer is released, and
-// only then is the second half reduced and whatever was staged published -- survivor handling never sits
-// between the barrier wake-up and the release, except for the few vector stores of a hit in the first half.
-__device__ __forceinline__ void epilogue_alt(ScoreShared* sh, const WorkItem* __restrict__ items, uint32_t n_items,
-                                             uint32_t tmem_base, int min_score, uint32_t e, uint32_t lane, uint32_t dbg) {
-  const uint32_t g = e / kEpiGroupWarps;               // == TMEM buffer
-  const uint32_t quarter = e & 3;                      // == warp % 4: TMEM lanes [32*quarter, +32)
-  const uint32_t col0 = ((e >> 2) & 1) * kEpiCols;     // which 128 of the tile's 256 columns
-  const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + g * kTileCols + col0;
-  const uint32_t full = ptx::smem_u32(&sh->t_full[g]), empty = ptx::smem_u32(&sh->t_empty[g]);
-  uint32_t ph = 0, gq = 0, mail_head = 0, mail_pub = 0, mail_tail_seen = 0;
-#ifdef SMB_TRACE
-  uint32_t tr_wait = 0, tr_hold = 0, tr_rest = 0, tr_tiles = 0;
-  const uint32_t tr_start = tr_clock();
-#endif
-  WorkItem w_next = blockIdx.x < n_items ? items[blockIdx.x] : WorkItem{};
-  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const WorkItem w = w_next;
-    if (it + gridDim.x < n_items) w_next = items[it + gridDim.x];  // a whole item ahead of its use
-    const uint32_t row_slot = w.row_slot0 + quarter * 32 + lane;
-    const uint32_t col_slot0 = w.col_slot0 + col0;
-    for (uint32_t t = 0; t < w.n_btiles; ++t) {
-      for (uint32_t mh = 0; mh < w.m_tiles; ++mh) {
-        if (((gq++) & 1u) != g) continue;  // the other group's tile
-        const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
-#ifdef SMB_TRACE
-        const uint32_t tr0 = tr_clock();
-#endif
-        ptx::mbar_wait(full, ph);
-        ph ^= 1;
-        ptx::tcgen05_fence_after();
-#ifdef SMB_TRACE
-        const uint32_t tr1 = tr_clock();
-#endif
-        uint32_t a[32], b[32];
-        ptx::tmem_ld_32x32b_x32_pair(taddr, a, b);
-        ptx::tmem_wait_ld();
-        scan_pass(sh, e, lane, a, b, min_score, rslot, cslot, mail_head, mail_tail_seen, dbg);
-        uint32_t c[32], d[32];
-        ptx::tmem_ld_32x32b_x32_pair(taddr + 2 * kRunCols, c, d);
-        ptx::tmem_wait_ld();
-        // the whole 32 x 128 slice is in registers (or already reduced): hand the buffer back to the MMA warp
-        ptx::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty);
-        // ptxas hoists the second pass' max tree (pure ALU) above the arrive, which would keep the buffer ~130 clk
-        // longer.  A branch on a value read after the arrive -- always taken: the host never sets dbg bit 31 --
-        // makes the pass control-dependent on something ptxas cannot schedule earlier.
-        const uint32_t tr2 = read_clock_ordered();
-        if (((tr2 & dbg) >> 31) == 0)
-          scan_pass(sh, e, lane, c, d, min_score, rslot, cslot + 2 * kRunCols, mail_head, mail_tail_seen, dbg);
-        if (mail_head != mail_pub) {
-          publish_mail(sh, e, lane, mail_head);
-          mail_pub = mail_head;
-        }
-#ifdef SMB_TRACE
-        tr_wait += tr1 - tr0;
-        tr_hold += tr2 - tr1;
-        tr_rest += tr_clock() - tr2;
-        ++tr_tiles;
-        if (blockIdx.x == 0 && (e & 7) == 0 && lane == 0 && gq - 1 < 64) {
-          g_tr[2][gq - 1][0] = tr0;
-          g_tr[2][gq - 1][1] = tr1;
-          g_tr[2][gq - 1][2] = tr2;
-          g_tr[2][gq - 1][3] = tr_clock();
-        }
-#endif
-      }
-    }
-  }
-#ifdef SMB_TRACE
-  if (blockIdx.x == 0 && lane == 0)
-    printf("EPI %2u tiles %u posts %u total %u | per own tile: total %.1f wait %.1f hold(ld+tree+ld) %.1f rest %.1f\n", e, tr_tiles,
-           mail_head, tr_clock() - tr_start, (float)(tr_clock() - tr_start) / (tr_tiles ? tr_tiles : 1),
-           (float)tr_wait / (tr_tiles ? tr_tiles : 1), (float)tr_hold / (tr_tiles ? tr_tiles : 1),
-           (float)tr_rest / (tr_tiles ? tr_tiles : 1));
-#endif
 }
 
 __global__ void __launch_bounds__(kScoreThreads, 1)
@@ -624,9 +367,9 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
       ptx::mbar_init(ptx::smem_u32(&sh->b_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&sh->b_empty[s]), 1);
     }
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&sh->t_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), kScout ? 1 : kHalfCommit ? kEpiGroupWarps / 2 : kEpiGroupWarps);
+      ptx::mbar_init(ptx::smem_u32(&sh->t_empty[s]), kEpiWarps);
     }
     for (int e = 0; e < kEpiWarps; ++e) {
       sh->mail_head[e] = 0;
@@ -689,7 +432,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
       }
       ptx::mbar_wait(ptx::smem_u32(&sh->a_full[as]), aph);
       ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
-      ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[kHalfCommit ? 2 * ts : ts]), tph ^ 1);
+      ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
       ptx::tcgen05_fence_after();
       uint64_t adesc0 = ptx::make_kmajor_sw128_desc(smem_a + as * kABytes);
       uint64_t bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
@@ -702,25 +445,10 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
 #endif
         const uint64_t adesc = adesc0 + mh * ((kABytes / 2) >> 4);
         const uint32_t d = tmem_base + ts * kTileCols;
-        if constexpr (kHalfCommit) {
-          constexpr uint32_t idesc_h = ptx::make_idesc_u8u8s32(kMTile, kTileCols / 2);
 #pragma unroll
-          for (uint32_t k = 0; k < kDim / 32; ++k) ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc_h, k);
-          ptx::umma_commit(ptx::smem_u32(&sh->t_full[2 * ts]));
-          // the second column half: its buffer half was released ~300 clk after the first one's
-          ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[2 * ts + 1]), tph ^ 1);
-          ptx::tcgen05_fence_after();
-          const uint64_t bdesc_h = bdesc + ((kBBytes / 2) >> 4);
-#pragma unroll
-          for (uint32_t k = 0; k < kDim / 32; ++k)
-            ptx::umma_i8(d + kTileCols / 2, adesc + k * 2, bdesc_h + k * 2, idesc_h, k);
-          ptx::umma_commit(ptx::smem_u32(&sh->t_full[2 * ts + 1]));
-        } else {
-#pragma unroll
-          for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
-            ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
-          ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
-        }
+        for (uint32_t k = 0; k < kDim / 32; ++k)  // UMMA K = 32 bytes; advance inside the swizzle atom
+          ptx::umma_i8(d, adesc + k * 2, bdesc + k * 2, idesc, k);
+        ptx::umma_commit(ptx::smem_u32(&sh->t_full[ts]));
         if (++ts == 2) { ts = 0; tph ^= 1; }
 #ifdef SMB_TRACE
         if (blockIdx.x == 0 && tr_tiles < 64) {
@@ -752,29 +480,17 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ptx::mbar_wait(ptx::smem_u32(&sh->b_full[bs]), bph);
           bdesc = ptx::make_kmajor_sw128_desc(smem_b + bs * kBBytes);
         }
-        ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[kHalfCommit ? 2 * ts : ts]), tph ^ 1);
+        ptx::mbar_wait(ptx::smem_u32(&sh->t_empty[ts]), tph ^ 1);
         ptx::tcgen05_fence_after();
-#ifdef SMB_TRACE
-        if (blockIdx.x == 0 && tr_tiles - 1 < 64) g_tr[0][tr_tiles - 1][2] = tr_clock();  // next buffer granted
-#endif
       }
     }
-  } else if (warp >= 4 && kEpiAlt) {
-    // ------------------------------------------------------------ filter epilogue, two alternating groups
-    epilogue_alt(sh, items, n_items, tmem_base, min_score, warp - 4, lane, dbg);
-    __syncwarp();
-    if (lane == 0) {
-      fence_cta();
-      atomicAdd(&sh->epi_done, 1u);
-    }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ filter epilogue (all warps on every tile)
+    // ------------------------------------------------------------ filter epilogue (8 warps)
     const uint32_t e = warp - 4;
     const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are visible to this warp
     const uint32_t col0 = (e >> 2) * kEpiCols;  // which 128 of the tile's 256 columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
     uint32_t ts = 0, tph = 0, mail_head = 0, mail_tail_seen = 0;
-    LaneLog ll{0ull, 0u, 0u};
 #ifdef SMB_TRACE
     uint32_t tr_wait = 0, tr_ld = 0, tr_rel = 0, tr_tree = 0, tr_post = 0, tr_tiles = 0, tr_posts = 0, tr_bp = 0, tr_bpn = 0, tr_store = 0, tr_pub = 0, tr_postonly = 0;
     const uint32_t tr_start = tr_clock();
@@ -793,11 +509,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
 #ifdef SMB_TRACE
           const uint32_t tr0 = tr_clock();
 #endif
-          const uint32_t tb = kHalfCommit ? 2 * ts + (e >> 2) : ts;  // this warp's (half-)buffer barriers
-          if constexpr (kScout)
-            ptx::bar_sync(1 + ts, 32 * (kEpiWarps + 1));  // the buffer's scout has seen t_full complete
-          else
-            ptx::mbar_wait(ptx::smem_u32(&sh->t_full[tb]), tph);
+          ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
 #ifdef SMB_TRACE
           const uint32_t tr1 = tr_clock();
@@ -821,12 +533,8 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           // once -- the hand-off latency (commit -> wake -> read -> arrive -> wake), not the arithmetic, is what
           // the two TMEM buffers have to cover
           ptx::tcgen05_fence_before();
-          if constexpr (kScout) {
-            ptx::bar_arrive(3 + ts, 32 * (kEpiWarps + 1));  // non-blocking; the scout arrives on t_empty for all eight
-          } else {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[tb]));
-          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[ts]));
           if (++ts == 2) { ts = 0; tph ^= 1; }
 #ifdef SMB_TRACE
           const uint32_t tr3 = tr_clock();
@@ -844,18 +552,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           tr_tree += tr4 - tr3;
           if (lanes && !(dbg & 4)) ++tr_posts;
 #endif
-          if constexpr (kDirect) {
-            if (lanes && !(dbg & 4)) {
-              const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
-              if (mc0 >= min_score) emit_run(acc, slog, ll, v0, min_score, rslot, cslot);
-              if (mc1 >= min_score) emit_run(acc, slog, ll, v1, min_score, rslot, cslot + kRunCols);
-              if constexpr (kRunsPerWarp == 4) {
-                if (mc2 >= min_score) emit_run(acc, slog, ll, v2, min_score, rslot, cslot + 2 * kRunCols);
-                if (mc3 >= min_score) emit_run(acc, slog, ll, v3, min_score, rslot, cslot + 3 * kRunCols);
-              }
-              __syncwarp();
-            }
-          } else if (lanes && !(dbg & 4)) {
+          if (lanes && !(dbg & 4)) {
             const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
                                 (mc3 >= min_score ? 8u : 0u);
             const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
@@ -901,8 +598,11 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
 #ifdef SMB_TRACE
             const uint32_t trs1 = tr_clock();
 #endif
-            // release-publish (see publish_mail): pairs with the insert warp's ld.acquire of the head
-            publish_mail(sh, e, lane, mail_head);
+            // Release-publish: __syncwarp orders every lane's payload stores before lane 0's st.release.cta, which
+            // pairs with the insert warp's ld.acquire.cta of the head (measured: no cost against the plain store it
+            // replaces, 3.11 POP/s either way -- the posting warp already waits longer for its vector stores to issue).
+            __syncwarp();
+            if (lane == 0) st_release_shared(&sh->mail_head[e], mail_head);
 #ifdef SMB_TRACE
             tr_pub += tr_clock() - trs1;
             tr_postonly += tr_clock() - tr4;
@@ -910,12 +610,11 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           }
 #ifdef SMB_TRACE
           tr_post += tr_clock() - tr4;
-          if (blockIdx.x == 0 && (e & 3) == 0 && lane == 0 && tr_tiles - 1 < 64) {
-            uint32_t (&g)[4] = g_tr[e == 0 ? 2 : 1][tr_tiles - 1];  // column half 0 / 1
-            g[0] = tr0;
-            g[1] = tr1;
-            g[2] = tr3;
-            g[3] = tr_clock();
+          if (blockIdx.x == 0 && e == 0 && lane == 0 && tr_tiles - 1 < 64) {
+            g_tr[2][tr_tiles - 1][0] = tr0;
+            g_tr[2][tr_tiles - 1][1] = tr1;
+            g_tr[2][tr_tiles - 1][2] = tr3;
+            g_tr[2][tr_tiles - 1][3] = tr_clock();
           }
 #endif
         }
@@ -927,33 +626,12 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
              tr_posts, tr_clock() - tr_start, (float)(tr_clock() - tr_start) / tr_tiles, (float)tr_wait / tr_tiles, (float)tr_ld / tr_tiles,
              (float)tr_rel / tr_tiles, (float)tr_tree / tr_tiles, (float)tr_post / tr_tiles, tr_bpn, tr_bp, (float)tr_postonly / (tr_posts ? tr_posts : 1), (float)tr_store / (tr_posts ? tr_posts : 1), (float)tr_pub / (tr_posts ? tr_posts : 1));
 #endif
-    if constexpr (kDirect) {  // retire this lane's log chunk (unused tail = zero entries) and report the count
-      if (slog.entries)
-        for (uint32_t x = 0; x < ll.left; ++x)
-          if (ll.pos + x < slog.capacity) slog.entries[ll.pos + x] = make_uint4(0, 0, 0, 0);
-      if (cand_counter && ll.cnt) atomicAdd(cand_counter, (unsigned long long)ll.cnt);
-    }
     __syncwarp();
     if (lane == 0) {
       fence_cta();
       atomicAdd(&sh->epi_done, 1u);
     }
-  } else if (kScout) {
-    // ------------------------------------------------------------ barrier proxies (warps 2, 3): one per TMEM buffer
-    const uint32_t b = warp - kInsertWarp0;
-    uint32_t ph = 0, gq = 0;
-    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const uint32_t tiles = items[it].n_btiles * items[it].m_tiles;
-      for (uint32_t q = 0; q < tiles; ++q) {
-        if (((gq++) & 1u) != b) continue;  // the other buffer's tile
-        ptx::mbar_wait(ptx::smem_u32(&sh->t_full[b]), ph);
-        ph ^= 1;
-        ptx::bar_arrive(1 + b, 32 * (kEpiWarps + 1));   // wake the eight epilogue warps
-        ptx::bar_sync(3 + b, 32 * (kEpiWarps + 1));     // all eight have read their slice of the buffer
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&sh->t_empty[b]));
-      }
-    }
-  } else if (!kDirect) {
+  } else {
     // ------------------------------------------------------------ insert (warps 2, 3)
     insert_loop(sh, acc, slog, min_score, warp - kInsertWarp0, lane, cand_counter, dbg);
   }
@@ -965,11 +643,9 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     __threadfence();
     const uint32_t t0 = g_tr[2][32][0];
     for (int q = 32; q < 44; ++q)
-      printf("tile %2d buf %d | MMA issue %6d..%6d next-buffer granted %6d | EPI wait-from %6d t_full %6d released %6d done %6d"
-             " | second half: wait-from %6d t_full %6d released %6d done %6d\n", q, q & 1,
-             (int)(g_tr[0][q][0] - t0), (int)(g_tr[0][q][1] - t0), (int)(g_tr[0][q][2] - t0), (int)(g_tr[2][q][0] - t0),
-             (int)(g_tr[2][q][1] - t0), (int)(g_tr[2][q][2] - t0), (int)(g_tr[2][q][3] - t0), (int)(g_tr[1][q][0] - t0),
-             (int)(g_tr[1][q][1] - t0), (int)(g_tr[1][q][2] - t0), (int)(g_tr[1][q][3] - t0));
+      printf("tile %2d buf %d | MMA issue %6d..%6d | EPI wait-from %6d t_full %6d released %6d done %6d\n", q, q & 1,
+             (int)(g_tr[0][q][0] - t0), (int)(g_tr[0][q][1] - t0), (int)(g_tr[2][q][0] - t0), (int)(g_tr[2][q][1] - t0),
+             (int)(g_tr[2][q][2] - t0), (int)(g_tr[2][q][3] - t0));
   }
 #endif
   if (warp == 2) {
@@ -979,7 +655,7 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
 }
 
 #ifdef SMB_TEST_ENGINES
-// Test-only device cross-check (compiled only with -DSMB_TEST_ENGINES, i.e. into tests' libsmb_test.so, never
+// Test-only device cross-check (compiled only with -DSMB_TEST_ENGINES, i.e. into the tests' libsmb_test.so, never
 // into the product libsmb.so): the same contract on CUDA cores (__dp4a), no tensor cores, no TMA.
 // =====================================================================================
 constexpr int kDp4aThreads = 256;

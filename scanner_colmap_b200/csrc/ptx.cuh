@@ -89,34 +89,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t pa
 #ifndef SMB_MBAR_SPIN_LIMIT
 #define SMB_MBAR_SPIN_LIMIT (1u << 22)
 #endif
-#ifndef SMB_MBAR_HINT_NS
-#define SMB_MBAR_HINT_NS 4000
-#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-#if defined(SMB_MBAR_BUSY_POLL)
+#ifdef SMB_MBAR_BUSY_POLL
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (SMB_MBAR_SPIN_LIMIT << 4)) __trap();
   }
-#elif defined(SMB_MBAR_TEST_SLEEP)
-  while (!mbar_test(bar, parity)) {
-    __nanosleep(SMB_MBAR_TEST_SLEEP);
-    if (++spins > (SMB_MBAR_SPIN_LIMIT << 4)) __trap();
-  }
 #else
-  while (!mbar_try_wait_hint(bar, parity, SMB_MBAR_HINT_NS)) {
+  while (!mbar_try_wait_hint(bar, parity, 4000u)) {
     if (++spins > SMB_MBAR_SPIN_LIMIT) __trap();
   }
 #endif
-}
-
-// ---------------------------------------------------------------- named barriers (hardware, no shared memory)
-// All 32 lanes of a warp execute these together; `threads` = total participating threads (arrivers + syncers).
-__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t threads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---------------------------------------------------------------- register reallocation between warpgroups
@@ -197,19 +180,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
-      : "memory");
-}
-
-
-// Two adjacent 32-column runs issued back to back from ONE asm statement: with two statements ptxas is free to
-// slide ALU work (and its temporaries) between the loads, which serialises them; a single x64 load needs a
-// contiguous 64-register tuple, which made ptxas spill.
-__device__ __forceinline__ void tmem_ld_32x32b_x32_pair(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];"
-      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]), "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
-      : "r"(taddr), "r"(taddr + 32u)
       : "memory");
 }
 

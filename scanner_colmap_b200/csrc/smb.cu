@@ -93,11 +93,27 @@ struct PinnedBuf {
 
 }  // namespace
 
+// A result lives in pinned, device-mapped host memory that decide_kernel writes directly (zero-copy): the match
+// lists, the per-pair {start, count} table (caller order) and a copy of the device counters.
 struct smb_result {
-  std::vector<PairOut> pair_out;  // per pair: start/count into matches
-  smb_match* matches = nullptr;   // pinned
+  size_t npairs = 0;
+  PairOut* pair_out = nullptr;  // pinned [pair_cap]
+  size_t pair_cap = 0;
+  smb_match* matches = nullptr;  // pinned [matches_cap]
   size_t matches_cap = 0;
+  size_t matches_limit = 0;      // entries the device may write in the current attempt (<= matches_cap)
+  unsigned long long* counters = nullptr;  // pinned [kNumCounters]: the device counters as of the end of the call
   size_t total = 0;
+  // between smb_match_pairs_begin and smb_result_wait
+  bool pending = false;
+  bool used_log = false;
+  size_t worst_case = 0;        // upper bound of the matches this call can produce
+  std::vector<uint64_t> keys;   // the call's pairs, kept for the (rare) repeat after an overflow
+  std::vector<cudaEvent_t> ev;  // profiling: 4 per sub-batch + 2
+  size_t n_subs = 0;
+  std::vector<uint8_t> sub_has_items;
+  uint64_t ops = 0;
+  uint32_t launches = 0, score_launches = 0, plan_uploaded = 0;
 };
 
 struct smb_handle {
@@ -107,9 +123,7 @@ struct smb_handle {
   float max_ratio_f = 0.f, max_distance_f = 0.f;
   Filter filter{};
   std::string err;
-  cudaStream_t stream = nullptr;      // uploads, accumulator clears, score kernels
-  cudaStream_t stream_out = nullptr;  // decide kernels and result copies (overlap the next sub-batch's scoring)
-  std::vector<cudaEvent_t> ev_pool;   // 4 per sub-batch: scored, decided, score begin/end
+  cudaStream_t stream = nullptr;      // synchronous uploads, accumulator clears, every kernel of a match call
   cudaStream_t stream_up = nullptr;   // asynchronous uploads (smb_put_images_async): copy engine under the score kernels
   static constexpr int kUpRing = 64;
   cudaEvent_t up_ev[kUpRing] = {};    // up_ev[t % kUpRing] fires when upload ticket t has landed
@@ -118,7 +132,8 @@ struct smb_handle {
   std::vector<uint32_t> plan_order;   // scratch of match_keys_impl
   std::vector<uint64_t> plan_ticket;
   uint64_t up_synced = 0;             // tickets <= this are known to have landed
-  cudaEvent_t ev[6] = {};  // total begin/end, scratch pairs for kernels
+  uint8_t up_fast[kUpRing] = {};      // ticket kind: 1 = device-to-device adoption (NVLink halo: lands within
+                                      // microseconds, never worth a sub-batch of its own), 0 = host upload over PCIe
   cudaEvent_t ev_ext = nullptr;  // marks the producer stream's position in smb_put_images_device_async
 
   // descriptor pool
@@ -137,24 +152,24 @@ struct smb_handle {
   DevBuf<PairMeta> d_pairs;
   DevBuf<WorkItem> d_items;
   DevBuf<TopTwo> d_acc;
-  DevBuf<uint2> d_out;
-  DevBuf<PairOut> d_pair_out;
-  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed
+  static constexpr int kNumCounters = 6;
+  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed,
+                                             // [4] result buffer overflowed
   DevBuf<uint4> d_log;                       // survivor log (kernels.cuh SurvivorLog)
   size_t log_cap = (size_t)16 << 20;         // entries; SMB_LOG_CAP overrides (tests force the overflow path)
-  PinnedBuf<PairMeta> h_pairs;
+  PinnedBuf<PairMeta> h_pairs;   // the plan the device copy (d_pairs / d_items) was fetched from
   PinnedBuf<WorkItem> h_items;
-  PinnedBuf<PairOut> h_pair_out;
-  PinnedBuf<unsigned long long> h_sub_counters;  // device counters as seen after each sub-batch
-  unsigned long long* h_counters = nullptr;  // pinned [4]
+  std::vector<PairMeta> plan_pairs;  // the plan being built; uploaded only if it differs from h_pairs / h_items
+  std::vector<WorkItem> plan_items;
+  size_t dev_plan_pairs = 0, dev_plan_items = 0;  // extent of the valid device copy (0 = none)
 
   std::vector<smb_result*> result_pool;
+  smb_result* inflight = nullptr;        // begun, not yet waited for
+  std::vector<std::pair<uint32_t, uint32_t>> pending_free;  // rows evicted while a call was in flight
   smb_timing timing{};
   size_t acc_budget = (size_t)64 << 20;  // accumulator slots per internal batch (16 B each; must stay < 2^32)
-  // Result-copy overlap (see match_keys_impl): what the last calls measured
-  double d2h_ms_per_mb = 0.0;            // device-to-host rate of the match copies (moving average)
-  double matches_per_pair = 0.0;         // matches per pair of the last call
-  double split_ms = -1.0;                // split a call in two when its predicted match copy takes longer (< 0: never)
+  double matches_per_pair = 0.0;         // most matches per pair any call produced so far (sizes the result buffer)
+  size_t result_cap_override = 0;        // SMB_RESULT_CAP: first-attempt capacity in matches (tests force the overflow repeat)
 
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   uint32_t dbg_flags = 0;  // SMB_DEBUG_FLAGS: bring-up timing experiments (see score_tcgen05_kernel)
@@ -226,8 +241,14 @@ Filter derive_filter(const std::vector<float>& lut, float max_ratio, float max_d
 
 int apply_options(smb_handle* h, const smb_options* opts) {
   if (!opts) return fail(h, SMB_EINVAL, "options pointer is null");
+#ifdef SMB_TEST_ENGINES
   if (opts->engine != SMB_ENGINE_TCGEN05 && opts->engine != SMB_ENGINE_DP4A)
     return fail(h, SMB_EINVAL, "unknown engine %d", opts->engine);
+#else
+  if (opts->engine != SMB_ENGINE_TCGEN05)
+    return fail(h, SMB_EINVAL, "engine %d is not part of this build (the product library has the tcgen05 engine only)",
+                opts->engine);
+#endif
   h->opts = *opts;
   h->max_ratio_f = (float)opts->max_ratio;        // double -> float exactly where COLMAP narrows
   h->max_distance_f = (float)opts->max_distance;
@@ -280,6 +301,7 @@ int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
   want = (want + kRowPad - 1) / kRowPad * kRowPad;
   if (want > 0xFFFFFF00ull) return fail(h, SMB_ENOMEM, "descriptor pool would exceed 2^32 rows");
   if (int rc = drain_uploads(h)) return rc;  // pending uploads target the old allocation
+  if (h->inflight) return fail(h, SMB_EINVAL, "the descriptor pool must grow while a match call is in flight: wait for it first");
   uint8_t* np = nullptr;
   SMB_CUDA(h, cudaMalloc(&np, want * kDim));
   if (h->pool) {
@@ -287,6 +309,7 @@ int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
     SMB_CUDA(h, cudaStreamSynchronize(h->stream));
     SMB_CUDA(h, cudaFree(h->pool));
   }
+  h->dev_plan_pairs = h->dev_plan_items = 0;  // (the plan holds pool rows, which are unchanged, but be safe)
   const uint32_t old_rows = h->pool_rows;
   h->pool = np;
   h->pool_rows = (uint32_t)want;
@@ -327,6 +350,29 @@ int drain_uploads(smb_handle* h) {
   return SMB_OK;
 }
 
+// Give an image's pool rows back.  No device synchronisation: every kernel that could read them belongs to a match
+// call, and a match call has either completed (smb_match_pairs / smb_result_wait return after the stream has been
+// synchronised) or is the one call in flight, in which case the rows are parked until its wait.  Copies into
+// recycled rows are ordered behind earlier work of the stream they are queued on; only an upload that is still
+// in flight INTO these rows on the upload stream has to be waited for.
+void poll_uploads(smb_handle* h) {  // tickets whose event has fired need no waiting any more
+  while (h->up_synced < h->up_issued && (h->up_open == 0 || h->up_synced + 1 < h->up_open) &&
+         cudaEventQuery(h->up_ev[(h->up_synced + 1) % smb_handle::kUpRing]) == cudaSuccess)
+    ++h->up_synced;
+  cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+}
+
+int retire_rows(smb_handle* h, const ImageEntry& e) {
+  if (e.up_seq > h->up_synced) poll_uploads(h);
+  if (e.up_seq > h->up_synced)
+    if (int rc = drain_uploads(h)) return rc;
+  if (h->inflight)
+    h->pending_free.emplace_back(e.row0, e.rows);
+  else
+    free_rows(h, e.row0, e.rows);
+  return SMB_OK;
+}
+
 int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_t d, cudaMemcpyKind kind,
                    cudaStream_t stream = nullptr, uint64_t up_seq = 0) {
   if (!stream) stream = h->stream;
@@ -335,13 +381,7 @@ int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_
   if (n > 0x7FFFFFFFu) return fail(h, SMB_EINVAL, "too many descriptors in one image: %zu", n);
   auto old = h->images.find(key);
   if (old != h->images.end()) {
-    // pairs already queued on the stream may still read the old rows; a pending upload may still write them
-    // (only then is the upload stream drained: draining it for every image of a device-async call would wait
-    // for that call's own producer, e.g. the halo recv, on the host)
-    SMB_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (old->second.up_seq > h->up_synced)
-      if (int rc = drain_uploads(h)) return rc;
-    free_rows(h, old->second.row0, old->second.rows);
+    if (int rc = retire_rows(h, old->second)) return rc;
     h->images.erase(old);
   }
   ImageEntry e;
@@ -382,12 +422,38 @@ smb_result* acquire_result(smb_handle* h) {
     h->result_pool.pop_back();
     return r;
   }
-  return new (std::nothrow) smb_result();
+  smb_result* r = new (std::nothrow) smb_result();
+  if (r && cudaMallocHost(&r->counters, smb_handle::kNumCounters * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaGetLastError();
+    delete r;
+    return nullptr;
+  }
+  return r;
 }
 
-struct BatchPlan {
-  size_t first, last;  // pair index range [first, last)
-};
+void destroy_result(smb_result* r) {
+  if (!r) return;
+  if (r->matches) cudaFreeHost(r->matches);
+  if (r->pair_out) cudaFreeHost(r->pair_out);
+  if (r->counters) cudaFreeHost(r->counters);
+  for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+  delete r;
+}
+
+template <typename T>
+bool reserve_pinned(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return true;
+  const size_t want = std::max<size_t>(std::max(need, *cap + *cap / 2), 1024);
+  T* q = nullptr;
+  if (cudaMallocHost(&q, want * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (*p) cudaFreeHost(*p);
+  *p = q;
+  *cap = want;
+  return true;
+}
 
 }  // namespace
 
@@ -431,7 +497,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
-  if (const char* e = getenv("SMB_RESULT_SPLIT_MS")) h->split_ms = atof(e);  // 0 = always split (tests), <0 = never
+  if (const char* e = getenv("SMB_RESULT_CAP")) h->result_cap_override = (size_t)strtoull(e, nullptr, 0);
   if (const char* e = getenv("SMB_ACC_BUDGET")) h->acc_budget = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 0));  // tests: force sub-batches
   int rc = SMB_OK;
   auto bail = [&](int code) {
@@ -449,11 +515,9 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   } while (0)
   SMB_CUDA_C(cudaSetDevice(cuda_device));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
   for (auto& e : h->up_ev) SMB_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
-  for (auto& e : h->ev) SMB_CUDA_C(cudaEventCreate(&e));
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -472,8 +536,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   }
   SMB_CUDA_C(cudaMalloc(&h->lut_dev, kLutSize * sizeof(float)));
   SMB_CUDA_C(cudaMemcpyAsync(h->lut_dev, h->lut_host.data(), kLutSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  SMB_CUDA_C(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
-  SMB_CUDA_C(cudaMallocHost(&h->h_counters, 4 * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMalloc(&h->d_counters, smb_handle::kNumCounters * sizeof(unsigned long long)));
   SMB_CUDA_C(cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
   SMB_CUDA_C(cudaStreamSynchronize(h->stream));
 #undef SMB_CUDA_C
@@ -489,31 +552,19 @@ void smb_destroy(smb_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->stream_out) cudaStreamSynchronize(h->stream_out);
   if (h->stream_up) cudaStreamSynchronize(h->stream_up);
-  for (smb_result* r : h->result_pool) {
-    if (r->matches) cudaFreeHost(r->matches);
-    delete r;
-  }
+  if (h->inflight) destroy_result(h->inflight);  // begun and never waited for: the stream is idle now
+  for (smb_result* r : h->result_pool) destroy_result(r);
   h->d_pairs.release();
   h->d_items.release();
   h->d_acc.release();
-  h->d_out.release();
-  h->d_pair_out.release();
   h->d_log.release();
   h->h_pairs.release();
   h->h_items.release();
-  h->h_pair_out.release();
-  h->h_sub_counters.release();
-  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->d_counters) cudaFree(h->d_counters);
-  if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->pool) cudaFree(h->pool);
-  for (auto& e : h->ev)
-    if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
-  if (h->stream_out) cudaStreamDestroy(h->stream_out);
   if (h->stream_up) cudaStreamDestroy(h->stream_up);
   for (auto& e : h->up_ev)
     if (e) cudaEventDestroy(e);
@@ -557,6 +608,7 @@ int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t
   if (h->up_issued - h->up_synced >= (uint64_t)smb_handle::kUpRing - 1)  // the event ring is about to wrap
     if (int rc = drain_uploads(h)) return rc;
   const uint64_t ticket = ++h->up_issued;
+  h->up_fast[ticket % smb_handle::kUpRing] = 0;  // host upload over PCIe: worth a sub-batch of its own
   OpenTicket open(h, ticket);
   for (size_t k = 0; k < count; ++k) {
     int rc = put_image_impl(h, image_ids[k], descs[k], ns[k], d, cudaMemcpyHostToDevice, h->stream_up, ticket);
@@ -596,6 +648,7 @@ int smb_put_images_device_async(smb_handle* h, const uint32_t* image_ids, const 
   if (h->up_issued - h->up_synced >= (uint64_t)smb_handle::kUpRing - 1)  // the event ring is about to wrap
     if (int rc = drain_uploads(h)) return rc;
   const uint64_t ticket = ++h->up_issued;
+  h->up_fast[ticket % smb_handle::kUpRing] = 1;  // device-to-device adoption: never splits a match call
   OpenTicket open(h, ticket);
   // the copies below must not start before the producer's queued work (e.g. the NCCL recv) has finished
   SMB_CUDA(h, cudaEventRecord(h->ev_ext, static_cast<cudaStream_t>(producer_stream)));
@@ -615,9 +668,7 @@ int smb_evict_image(smb_handle* h, uint32_t image_id) {
   auto it = h->images.find(image_id);
   if (it == h->images.end()) return fail(h, SMB_EINVAL, "image %u is not cached", image_id);
   SMB_CUDA(h, cudaSetDevice(h->device));
-  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (int rc = drain_uploads(h)) return rc;
-  free_rows(h, it->second.row0, it->second.rows);
+  if (int rc = retire_rows(h, it->second)) return rc;  // no device synchronisation (see retire_rows)
   h->images.erase(it);
   return SMB_OK;
 }
@@ -625,8 +676,8 @@ int smb_evict_image(smb_handle* h, uint32_t image_id) {
 int smb_clear_images(smb_handle* h) {
   if (!h) return SMB_EINVAL;
   SMB_CUDA(h, cudaSetDevice(h->device));
-  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (int rc = drain_uploads(h)) return rc;
+  if (h->inflight) return fail(h, SMB_EINVAL, "smb_clear_images while a match call is in flight");
+  if (int rc = drain_uploads(h)) return rc;  // pending uploads still write pool rows
   h->images.clear();
   h->free_list.clear();
   if (h->pool_rows) h->free_list.emplace(0u, h->pool_rows);
@@ -642,66 +693,43 @@ int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** de
   return SMB_OK;
 }
 
-// One smb_match_pairs call.  The pair list is cut into a few sub-batches that flow through two streams:
-//   main stream : [plan upload] -> per sub-batch: zero the accumulators, score (+ runner-up) and decide kernels
-//   out  stream : per sub-batch, once decided: header copy, then exactly its matches -> pinned host memory
-// so the result copies of sub-batch k run on the copy engine under the scoring of sub-batch k+1.  (Running
-// the decide kernels on the second stream as well was measured slower: the persistent score CTAs own every
-// SM, so a concurrent decide kernel only delays the next score kernel's CTAs.)
-static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */, size_t npairs, smb_result** out,
-                           bool use_log, bool* overflowed) {
-  *overflowed = false;
-  *out = nullptr;
-  SMB_CUDA(h, cudaSetDevice(h->device));
+// One match call = enqueue (everything the device needs, no host decision in between) + finish (one stream
+// synchronisation, then the counters the device left in pinned memory say whether the attempt stands).
+//
+//   [plan fetch, only if the plan differs from the one already on the device]
+//   per sub-batch: zero the accumulators -> score_tcgen05_kernel -> runner_up_kernel -> decide_kernel
+//   copy of the 48-byte counter block
+//
+// all on the handle's main stream.  decide_kernel writes the matches and the per-pair {start, count} table straight
+// into the result's pinned host memory (zero-copy), so when the stream is idle the result is complete: no staging
+// buffer, no device-to-host copy of the matches, no "how many matches?" round trip.
+//
+// Sub-batches exist (a) to bound the accumulator footprint and (b) to start on pairs whose images have landed while
+// later HOST uploads (smb_put_images_async, PCIe) are still in flight: a new sub-batch begins where a pair needs a
+// newer, still pending host-upload ticket than all pairs before it, and each sub-batch's kernels wait on the
+// device for their own ticket only.  A pending device-to-device adoption (smb_put_images_device_async: the NVLink
+// halo, microseconds) never splits a call -- every extra score launch pays its own tail (~0.2 ms measured), more
+// than such a wait costs.
+static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t matches_want) {
+  const uint64_t* keys = res->keys.data();
+  const size_t npairs = res->npairs;
   const bool prof = h->opts.profile != 0;
   const bool cc = h->opts.cross_check != 0;
-  std::memset(&h->timing, 0, sizeof h->timing);
 
-  smb_result* res = acquire_result(h);
-  if (!res) return fail(h, SMB_ENOMEM, "out of host memory");
-  auto give_back = [&](int code) {
-    h->result_pool.push_back(res);
-    return code;
-  };
-  res->pair_out.assign(npairs, PairOut{0, 0});
-  res->total = 0;
-  if (npairs == 0) {
-    *out = res;
-    return SMB_OK;
-  }
-  if (npairs > 0x7FFFFFFFull) return give_back(fail(h, SMB_EINVAL, "too many pairs in one call"));
-
-  // uploads that have landed since the last look need no waiting (and no sub-batch of their own)
-  while (h->up_synced < h->up_issued &&
-         cudaEventQuery(h->up_ev[(h->up_synced + 1) % smb_handle::kUpRing]) == cudaSuccess)
-    ++h->up_synced;
-  cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+  poll_uploads(h);  // uploads that have landed since the last look need no waiting (and no sub-batch of their own)
 
   // ---- plan: metas, work items, sub-batches
-  struct Sub { size_t first, last, item0, items, acc, out_cap; uint64_t ticket; };
+  struct Sub { size_t first, last, item0, items, acc; uint64_t split_ticket, wait_ticket; };
   std::vector<Sub> subs;
-  if (cudaSuccess != h->h_pairs.reserve(npairs)) return give_back(fail(h, SMB_ENOMEM, "pinned allocation failed"));
-  // Sub-batches exist (a) to bound the accumulator footprint and (b) to start on pairs whose images have landed
-  // while later asynchronous uploads (smb_put_images_async) are still in flight: a new sub-batch begins where
-  // a pair needs a newer, still pending upload ticket than all pairs before it, and each sub-batch's kernels
-  // wait for their own ticket only.  Splitting further to overlap result copies with scoring was measured
-  // slower (855 resident pairs: 5.94 ms in 4 sub-batches vs 5.77 ms in one: every extra score launch pays its
-  // own tail), so with everything resident a call is one sub-batch unless the accumulator budget says otherwise.
-  // Optional exception (SMB_RESULT_SPLIT_MS=<ms>, off by default): when the predicted device-to-host copy of the
-  // matches exceeds that many milliseconds -- from the copy rate and matches per pair the previous calls measured --
-  // the first 80 % of the pairs form their own sub-batch, so their matches cross PCIe under the scoring of the
-  // rest.  Measured on 8 GPUs with a 0.5 ms threshold: 1.073 M vs 1.075 M pairs/s, i.e. no gain (the extra
-  // launches cost ~0.2 ms: runner-up, decide and the accumulator reset sit between the two score kernels), hence
-  // off; kept because it is the cheap answer where result copies do dominate (many matches per pair, slow links).
-  size_t target_pairs = npairs;
-  if (h->split_ms >= 0.0 && npairs >= 64) {
-    const double pred_ms = h->matches_per_pair * (double)npairs * sizeof(smb_match) * 1e-6 * h->d2h_ms_per_mb;
-    if (pred_ms > h->split_ms || h->split_ms == 0.0) target_pairs = (npairs * 4 + 4) / 5;
-  }
+  std::vector<PairMeta>& pm = h->plan_pairs;
+  std::vector<WorkItem>& wi = h->plan_items;
+  pm.resize(npairs);
+  wi.clear();
   const size_t sub_budget = h->acc_budget;
-  size_t out_cap = 0, n_items_total = 0, max_acc = 0;
+  size_t out_cap = 0, max_acc = 0;
   uint64_t ops = 0;
-  // Planned order: with uploads still in flight, pairs are taken in the order their images land (stable), so an
+  auto is_host_ticket = [&](uint64_t t) { return t > h->up_synced && !h->up_fast[t % smb_handle::kUpRing]; };
+  // Planned order: with host uploads still in flight, pairs are taken in the order their images land (stable), so an
   // early pair listed after a late one does not wait for the late one's upload.  order[q] = caller index.
   std::vector<uint32_t>& order = h->plan_order;
   order.clear();
@@ -713,8 +741,11 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
       auto i1 = h->images.find(keys[2 * p]);
       auto i2 = h->images.find(keys[2 * p + 1]);
       uint64_t t = 0;
-      if (i1 != h->images.end() && i2 != h->images.end()) t = std::max(i1->second.up_seq, i2->second.up_seq);
-      tk[p] = t > h->up_synced ? t : 0;
+      if (i1 != h->images.end() && i2 != h->images.end()) {
+        if (is_host_ticket(i1->second.up_seq)) t = i1->second.up_seq;
+        if (is_host_ticket(i2->second.up_seq)) t = std::max(t, i2->second.up_seq);
+      }
+      tk[p] = t;
       if (p && tk[p] < tk[p - 1]) sorted = false;
     }
     if (!sorted) {
@@ -730,253 +761,291 @@ static int match_keys_impl(smb_handle* h, const uint64_t* keys /* [npairs][2] */
       auto i1 = h->images.find(keys[2 * src]);
       auto i2 = h->images.find(keys[2 * src + 1]);
       if (i1 == h->images.end() || i2 == h->images.end())
-        return give_back(fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", src,
-                              (unsigned long long)(i1 == h->images.end() ? keys[2 * src] : keys[2 * src + 1])));
+        return fail(h, SMB_EINVAL, "pair %zu names image %llu which is not cached", src,
+                    (unsigned long long)(i1 == h->images.end() ? keys[2 * src] : keys[2 * src + 1]));
       const ImageEntry &a = i1->second, &b = i2->second;
       const uint64_t ticket = std::max(a.up_seq, b.up_seq);
+      uint64_t host_ticket = 0;
+      if (is_host_ticket(a.up_seq)) host_ticket = a.up_seq;
+      if (is_host_ticket(b.up_seq)) host_ticket = std::max(host_ticket, b.up_seq);
       const size_t need = (size_t)a.n + b.n;
-      const bool newer_upload = ticket > cur.ticket && ticket > h->up_synced;
-      if (p > cur.first && (cur.acc + need > sub_budget || p - cur.first >= target_pairs || newer_upload)) {
+      const bool newer_upload = host_ticket > cur.split_ticket;
+      if (p > cur.first && (cur.acc + need > sub_budget || newer_upload)) {
         cur.last = p;
         subs.push_back(cur);
-        cur = Sub{p, 0, cur.item0 + cur.items, 0, 0, 0, cur.ticket};
+        cur = Sub{p, 0, wi.size(), 0, 0, cur.split_ticket, cur.wait_ticket};
       }
-      cur.ticket = std::max(cur.ticket, ticket);
-      PairMeta& m = h->h_pairs.p[p];
+      cur.split_ticket = std::max(cur.split_ticket, host_ticket);
+      if (ticket > h->up_synced) cur.wait_ticket = std::max(cur.wait_ticket, ticket);
+      PairMeta& m = pm[p];
       m.a_row0 = a.row0;
       m.n1 = a.n;
       m.b_row0 = b.row0;
       m.n2 = b.n;
       m.acc_off = (uint32_t)cur.acc;
-      m.out_slot = (uint32_t)p;
+      m.out_slot = (uint32_t)src;  // decide_kernel fills the caller-order table directly
       cur.acc += need;
-      if (a.n && b.n) cur.items += (a.n + kStripRows - 1) / kStripRows;
-      cur.out_cap += cc ? std::min(a.n, b.n) : a.n;
+      // work items: one per 256-row strip; the strips of a pair stay adjacent so that concurrently running CTAs
+      // stream the same image 2 out of L2
+      if (a.n && b.n) {
+        const uint32_t n_btiles = (b.n + kTileCols - 1) / kTileCols;
+        for (uint32_t r = 0; r < a.n; r += kStripRows)
+          wi.push_back(WorkItem{a.row0 + r, b.row0, n_btiles, a.n - r > (uint32_t)kMTile ? 2u : 1u, m.acc_off + r,
+                                m.acc_off + a.n, (uint32_t)(p - cur.first), 0u});
+      }
+      out_cap += cc ? std::min(a.n, b.n) : a.n;
       ops += 2ull * a.n * b.n * kDim;
     }
     cur.last = npairs;
     subs.push_back(cur);
-    for (const Sub& sb : subs) {
-      n_items_total += sb.items;
+    for (size_t k = 0; k < subs.size(); ++k) {
+      Sub& sb = subs[k];
+      sb.items = (k + 1 < subs.size() ? subs[k + 1].item0 : wi.size()) - sb.item0;
       max_acc = std::max(max_acc, sb.acc);
-      out_cap += sb.out_cap;
+      // ragged sets: largest column counts first inside each sub-batch (stable: a pair's strips stay adjacent)
+      WorkItem* it0 = wi.data() + sb.item0;
+      bool uniform = true;
+      for (size_t x = 1; x < sb.items && uniform; ++x) uniform = it0[x].n_btiles == it0[0].n_btiles;
+      if (!uniform)
+        std::stable_sort(it0, it0 + sb.items, [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
     }
   }
-  if (out_cap > 0xFFFFFFFFull) return give_back(fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call"));
+  if (out_cap > 0xFFFFFF00ull) return fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call");
+  res->worst_case = out_cap;
+  const size_t n_items_total = wi.size();
   const size_t acc_region = (max_acc + 15) / 16 * 16;
-  use_log = use_log && h->log_cap && h->opts.engine == SMB_ENGINE_TCGEN05;
+  use_log = use_log && h->log_cap;
+#ifdef SMB_TEST_ENGINES
+  use_log = use_log && h->opts.engine == SMB_ENGINE_TCGEN05;
+#endif
+  res->used_log = use_log;
 
+  // ---- result buffers (pinned, written by the device): sized from what earlier calls produced, worst case on retry
+  if (matches_want == 0) {
+    matches_want = h->matches_per_pair > 0.0 ? (size_t)(1.5 * h->matches_per_pair * (double)npairs) + 4096 : out_cap / 2 + 4096;
+    if (h->result_cap_override) matches_want = h->result_cap_override;
+  }
+  matches_want = std::min(std::max<size_t>(matches_want, 1), std::max<size_t>(out_cap, 1));
+  res->matches_limit = matches_want;
+  if (!reserve_pinned(&res->matches, &res->matches_cap, matches_want) || !reserve_pinned(&res->pair_out, &res->pair_cap, npairs))
+    return fail(h, SMB_ENOMEM, "pinned result allocation failed (%zu matches, %zu pairs)", matches_want, npairs);
   if (cudaSuccess != h->d_pairs.reserve(npairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(n_items_total, 1)) ||
-      cudaSuccess != h->d_acc.reserve(std::max<size_t>(acc_region, 1)) ||
-      cudaSuccess != h->d_out.reserve(std::max<size_t>(out_cap, 1)) || cudaSuccess != h->d_pair_out.reserve(npairs) ||
-      cudaSuccess != h->h_pair_out.reserve(npairs) || cudaSuccess != h->h_items.reserve(std::max<size_t>(n_items_total, 1)) ||
-      cudaSuccess != h->h_sub_counters.reserve(4 * subs.size()) ||
+      cudaSuccess != h->d_acc.reserve(std::max<size_t>(acc_region, 1)) || cudaSuccess != h->h_pairs.reserve(npairs) ||
+      cudaSuccess != h->h_items.reserve(std::max<size_t>(n_items_total, 1)) ||
       (use_log && cudaSuccess != h->d_log.reserve(h->log_cap))) {
     cudaGetLastError();
-    return give_back(fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu out=%zu)", npairs,
-                          acc_region, out_cap));
+    return fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu)", npairs, acc_region);
   }
-  // pinned result buffer: starts at a quarter of the worst case (min(n1, n2) matches per pair), grown on demand
-  auto ensure_matches = [&](size_t need, size_t keep) -> bool {
-    if (need <= res->matches_cap) return true;
-    const size_t want = std::max<size_t>(std::max(need, res->matches_cap * 2), 4096);
-    smb_match* q = nullptr;
-    if (cudaMallocHost(&q, want * sizeof(smb_match)) != cudaSuccess) return false;
-    if (res->matches) {
-      if (keep) std::memcpy(q, res->matches, keep * sizeof(smb_match));
-      cudaFreeHost(res->matches);
+  if (prof) {
+    while (res->ev.size() < 4 * subs.size() + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(h, SMB_ECUDA, "cudaEventCreate failed");
+      res->ev.push_back(e);
     }
-    res->matches = q;
-    res->matches_cap = want;
-    return true;
-  };
-  if (!ensure_matches(out_cap / 4 + 1, 0)) return give_back(fail(h, SMB_ENOMEM, "pinned result allocation failed"));
-  while (h->ev_pool.size() < 4 * subs.size()) {
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return give_back(fail(h, SMB_ECUDA, "cudaEventCreate failed"));
-    h->ev_pool.push_back(e);
   }
+  res->n_subs = subs.size();
+  res->sub_has_items.assign(subs.size(), 0);
+  res->ops = ops;
+  res->launches = res->score_launches = res->plan_uploaded = 0;
 
-  // work items: one per 256-row strip, pairs in caller order (strips of a pair stay adjacent so concurrently
-  // running CTAs stream the same image 2 out of L2), largest column counts first inside each sub-batch
-  for (const Sub& sb : subs) {
-    WorkItem* it0 = h->h_items.p + sb.item0;
-    size_t ni = 0;
-    for (size_t p = sb.first; p < sb.last; ++p) {
-      const PairMeta& m = h->h_pairs.p[p];
-      if (!m.n1 || !m.n2) continue;
-      const uint32_t n_btiles = (m.n2 + kTileCols - 1) / kTileCols;
-      for (uint32_t r = 0; r < m.n1; r += kStripRows)
-        it0[ni++] = WorkItem{m.a_row0 + r, m.b_row0, n_btiles, m.n1 - r > (uint32_t)kMTile ? 2u : 1u,
-                             m.acc_off + r, m.acc_off + m.n1, (uint32_t)(p - sb.first), 0u};
-    }
-    bool uniform = true;
-    for (size_t x = 1; x < ni && uniform; ++x) uniform = it0[x].n_btiles == it0[0].n_btiles;
-    if (!uniform) std::stable_sort(it0, it0 + ni, [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
-  }
-
-  cudaStream_t st = h->stream, so = h->stream_out;
-#define SMB_CUDA_R(expr)                                                                                  \
-  do {                                                                                                    \
-    cudaError_t e__ = (expr);                                                                             \
-    if (e__ != cudaSuccess) {                                                                             \
-      cudaStreamSynchronize(st);                                                                          \
-      cudaStreamSynchronize(so);                                                                          \
-      return give_back(fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
-    }                                                                                                     \
+  cudaStream_t st = h->stream;
+#define SMB_CUDA_R(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      cudaStreamSynchronize(st);                                                                 \
+      return fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                            \
   } while (0)
 
-  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[0], st));
-  SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  {  // plan upload by a kernel reading pinned host memory (not the copy engine, see fetch_words_kernel)
+  // ---- plan upload, skipped when the device already holds exactly this plan (steady state: same pairs, same rows).
+  // The device reads the pinned plan directly (UVA): a cudaMemcpyAsync would queue behind whatever descriptor uploads
+  // are already in the host->device copy engine's FIFO and stall the score kernel it feeds.
+  const bool same_plan = h->dev_plan_pairs == npairs && h->dev_plan_items == n_items_total &&
+                         std::memcmp(h->h_pairs.p, pm.data(), npairs * sizeof(PairMeta)) == 0 &&
+                         (n_items_total == 0 || std::memcmp(h->h_items.p, wi.data(), n_items_total * sizeof(WorkItem)) == 0);
+  if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[0], st));
+  SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, smb_handle::kNumCounters * sizeof(unsigned long long), st));
+  if (!same_plan) {
+    h->dev_plan_pairs = h->dev_plan_items = 0;  // invalid until the fetch below has been queued
+    std::memcpy(h->h_pairs.p, pm.data(), npairs * sizeof(PairMeta));
+    if (n_items_total) std::memcpy(h->h_items.p, wi.data(), n_items_total * sizeof(WorkItem));
     static_assert(sizeof(PairMeta) % 4 == 0 && sizeof(WorkItem) % 4 == 0, "plan structs are whole words");
-    const size_t wp = npairs * sizeof(PairMeta) / 4, wi = n_items_total * sizeof(WorkItem) / 4;
+    const size_t wp = npairs * sizeof(PairMeta) / 4, ww = n_items_total * sizeof(WorkItem) / 4;
     fetch_words_kernel<<<(unsigned)std::min<size_t>((wp + 255) / 256, 512), 256, 0, st>>>(
         reinterpret_cast<uint32_t*>(h->d_pairs.p), reinterpret_cast<const uint32_t*>(h->h_pairs.p), wp);
-    if (wi)
-      fetch_words_kernel<<<(unsigned)std::min<size_t>((wi + 255) / 256, 512), 256, 0, st>>>(
-          reinterpret_cast<uint32_t*>(h->d_items.p), reinterpret_cast<const uint32_t*>(h->h_items.p), wi);
+    if (ww)
+      fetch_words_kernel<<<(unsigned)std::min<size_t>((ww + 255) / 256, 512), 256, 0, st>>>(
+          reinterpret_cast<uint32_t*>(h->d_items.p), reinterpret_cast<const uint32_t*>(h->h_items.p), ww);
     SMB_CUDA_R(cudaGetLastError());
-    h->timing.total_launches += wi ? 2 : 1;
+    res->launches += ww ? 2 : 1;
+    res->plan_uploaded = 1;
+    h->dev_plan_pairs = npairs;
+    h->dev_plan_items = n_items_total;
   }
   const SurvivorLog slog{use_log ? h->d_log.p : nullptr, h->d_counters + 2, (unsigned long long)h->log_cap};
-  if (h->opts.engine == SMB_ENGINE_TCGEN05 && n_items_total && !h->tmap_valid)
-    return give_back(fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised"));
+  if (n_items_total && !h->tmap_valid) return fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised");
 
+  uint64_t waited = h->up_synced;
   for (size_t k = 0; k < subs.size(); ++k) {
     const Sub& sb = subs[k];
-    cudaEvent_t ev_scored = h->ev_pool[4 * k], ev_decided = h->ev_pool[4 * k + 1], ev_s0 = h->ev_pool[4 * k + 2],
-                ev_s1 = h->ev_pool[4 * k + 3];
-    TopTwo* acc = h->d_acc.p;  // reused by every sub-batch: all kernels touching it are ordered on the main stream
-    // tickets complete in order on the upload stream: waiting for the newest one of this sub-batch is enough
-    if (sb.ticket > h->up_synced && (k == 0 || sb.ticket > subs[k - 1].ticket))
-      SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[sb.ticket % smb_handle::kUpRing], 0));
+    TopTwo* acc = h->d_acc.p;  // reused by every sub-batch: all kernels touching it are ordered on the stream
+    // tickets complete in order on the upload stream: waiting for the newest one this sub-batch needs is enough
+    if (sb.wait_ticket > waited) {
+      SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[sb.wait_ticket % smb_handle::kUpRing], 0));
+      waited = sb.wait_ticket;
+    }
     if (sb.acc) SMB_CUDA_R(cudaMemsetAsync(acc, 0, sb.acc * sizeof(TopTwo), st));
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[2 + 4 * k], st));
     if (sb.items) {
-      if (prof) SMB_CUDA_R(cudaEventRecord(ev_s0, st));
+      res->sub_has_items[k] = 1;
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
-      if (h->opts.engine == SMB_ENGINE_TCGEN05) {
+#ifdef SMB_TEST_ENGINES
+      if (h->opts.engine == SMB_ENGINE_DP4A) {
+        const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms * 4);
+        score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p + sb.item0, (uint32_t)sb.items,
+                                                         h->d_pairs.p + sb.first, acc, h->filter.min_score, cand);
+      } else
+#endif
+      {
         if (use_log) SMB_CUDA_R(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), st));
         const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms);  // persistent CTAs
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p + sb.item0, (uint32_t)sb.items,
                                                                           h->d_pairs.p + sb.first, acc, slog,
                                                                           h->filter.min_score, cand, h->dbg_flags);
-        if (use_log) {
-          SMB_CUDA_R(cudaGetLastError());
-          runner_up_kernel<<<(unsigned)h->num_sms * 8, 256, 0, st>>>(h->d_log.p, h->d_counters + 2, h->d_counters + 3,
-                                                                    (unsigned long long)h->log_cap, acc);
-          h->timing.total_launches++;
-        }
-      } else {
-        const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms * 4);
-        score_dp4a_kernel<<<grid, kDp4aThreads, 0, st>>>(h->pool, h->d_items.p + sb.item0, (uint32_t)sb.items,
-                                                         h->d_pairs.p + sb.first, acc, h->filter.min_score, cand);
       }
       SMB_CUDA_R(cudaGetLastError());
-      h->timing.score_launches++;
-      h->timing.total_launches++;
-      if (prof) SMB_CUDA_R(cudaEventRecord(ev_s1, st));
+      res->score_launches++;
+      res->launches++;
     }
-    decide_kernel<<<(unsigned)(sb.last - sb.first), kDecideThreads, 0, st>>>(h->d_pairs.p + sb.first, acc, h->lut_dev,
-                                                                             h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
-                                                                             h->d_out.p, ~0ull, h->d_counters, h->d_counters + 3, h->d_pair_out.p);
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[3 + 4 * k], st));
+    if (sb.items && use_log) {
+      runner_up_kernel<<<(unsigned)h->num_sms * 8, 256, 0, st>>>(h->d_log.p, h->d_counters + 2, h->d_counters + 3,
+                                                                (unsigned long long)h->log_cap, acc);
+      SMB_CUDA_R(cudaGetLastError());
+      res->launches++;
+    }
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[4 + 4 * k], st));
+    decide_kernel<<<(unsigned)(sb.last - sb.first), kDecideThreads, 0, st>>>(
+        h->d_pairs.p + sb.first, acc, h->lut_dev, h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
+        reinterpret_cast<uint2*>(res->matches), (unsigned long long)res->matches_limit, h->d_counters, h->d_counters + 4,
+        res->pair_out);
     SMB_CUDA_R(cudaGetLastError());
-    h->timing.total_launches++;
-    SMB_CUDA_R(cudaEventRecord(ev_scored, st));
-    // ---- out stream: the header of this sub-batch (match total so far + its pairs' ranges)
-    SMB_CUDA_R(cudaStreamWaitEvent(so, ev_scored, 0));
-    SMB_CUDA_R(cudaMemcpyAsync(h->h_sub_counters.p + 4 * k, h->d_counters, 4 * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, so));
-    SMB_CUDA_R(cudaMemcpyAsync(h->h_pair_out.p + sb.first, h->d_pair_out.p + sb.first,
-                               (sb.last - sb.first) * sizeof(PairOut), cudaMemcpyDeviceToHost, so));
-    SMB_CUDA_R(cudaEventRecord(ev_decided, so));
+    res->launches++;
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[5 + 4 * k], st));
   }
-
-  // ---- results: as each sub-batch's header lands, copy exactly the matches it produced
-  size_t copied = 0, last_copy_bytes = 0;
-  std::chrono::steady_clock::time_point last_copy_t0{};
-  for (size_t k = 0; k < subs.size(); ++k) {
-    SMB_CUDA_R(cudaEventSynchronize(h->ev_pool[4 * k + 1]));
-    const size_t upto = (size_t)h->h_sub_counters.p[4 * k];  // decide kernels reserve contiguously, in stream order
-    if (upto > out_cap || upto < copied) {
-      cudaStreamSynchronize(st);
-      cudaStreamSynchronize(so);
-      return give_back(fail(h, SMB_ECUDA, "internal error: %zu matches exceed capacity %zu", upto, out_cap));
-    }
-    if (upto > res->matches_cap) {
-      SMB_CUDA_R(cudaStreamSynchronize(so));  // earlier copies must have landed before the buffer moves
-      if (!ensure_matches(upto, copied)) {
-        cudaStreamSynchronize(st);
-        return give_back(fail(h, SMB_ENOMEM, "pinned result allocation of %zu matches failed", upto));
-      }
-    }
-    if (upto > copied)
-      SMB_CUDA_R(cudaMemcpyAsync(res->matches + copied, h->d_out.p + copied, (upto - copied) * sizeof(smb_match),
-                                 cudaMemcpyDeviceToHost, so));
-    if (k + 1 == subs.size()) {
-      last_copy_bytes = (upto - copied) * sizeof(smb_match);
-      last_copy_t0 = std::chrono::steady_clock::now();
-    }
-    copied = upto;
-  }
-  if (prof) SMB_CUDA_R(cudaEventRecord(h->ev[1], so));
-  SMB_CUDA_R(cudaStreamSynchronize(so));
-  SMB_CUDA_R(cudaStreamSynchronize(st));
-  if (last_copy_bytes >= (1u << 20)) {  // the copy just waited for: header of the last sub-batch -> all matches landed
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - last_copy_t0).count();
-    const double rate = ms / (last_copy_bytes * 1e-6);
-    h->d2h_ms_per_mb = h->d2h_ms_per_mb > 0.0 ? 0.75 * h->d2h_ms_per_mb + 0.25 * rate : rate;
-  }
-  const unsigned long long* last = h->h_sub_counters.p + 4 * (subs.size() - 1);
-  if (last[3]) {  // the survivor log overflowed: this attempt's runner-up keys are incomplete
-    *overflowed = true;
-    return give_back(SMB_OK);
-  }
-  if (order.empty())
-    std::memcpy(res->pair_out.data(), h->h_pair_out.p, npairs * sizeof(PairOut));
-  else
-    for (size_t q = 0; q < npairs; ++q) res->pair_out[order[q]] = h->h_pair_out.p[q];
-  res->total = copied;
-  h->matches_per_pair = (double)copied / (double)npairs;
-  if (prof) {
-    float ms = 0.f, score_ms = 0.f;
-    SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    h->timing.total_ms = ms;
-    for (size_t k = 0; k < subs.size(); ++k) {
-      if (!subs[k].items) continue;
-      SMB_CUDA_R(cudaEventElapsedTime(&ms, h->ev_pool[4 * k + 2], h->ev_pool[4 * k + 3]));
-      score_ms += ms;
-    }
-    h->timing.score_ms = score_ms;
-    h->timing.decide_ms = 0.f;  // overlapped with scoring on the second stream; see total_ms
-    h->timing.candidates = last[1];
-  }
-  h->timing.ops = ops;
+  SMB_CUDA_R(cudaMemcpyAsync(res->counters, h->d_counters, smb_handle::kNumCounters * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
+  if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[1], st));
 #undef SMB_CUDA_R
+  return SMB_OK;
+}
+
+static void flush_pending_free(smb_handle* h) {
+  for (auto& f : h->pending_free) free_rows(h, f.first, f.second);
+  h->pending_free.clear();
+}
+
+// Wait for an enqueued call and decide whether its results stand.  Two (rare) reasons to repeat it: the survivor log
+// overflowed (adversarial inputs where almost every score survives: repeat with the returning two-stage insertion),
+// or the matches did not fit the result buffer (repeat with the worst-case size).
+static int finish_match(smb_handle* h, smb_result* res) {
+  for (int attempt = 0;; ++attempt) {
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(h, SMB_ECUDA, "match call failed on the device: %s", cudaGetErrorString(e));
+    const unsigned long long* c = res->counters;
+    const bool log_over = res->used_log && c[3] != 0, out_over = c[4] != 0;
+    if (!log_over && !out_over) break;
+    if (attempt >= 2) return fail(h, SMB_ECUDA, "internal error: match call still overflows after two repeats");
+    int rc = enqueue_match(h, res, res->used_log && !log_over, out_over ? res->worst_case : res->matches_limit);
+    if (rc != SMB_OK) return rc;
+  }
+  res->total = (size_t)res->counters[0];
+  if (res->npairs) h->matches_per_pair = std::max(h->matches_per_pair, (double)res->total / (double)res->npairs);
+  std::memset(&h->timing, 0, sizeof h->timing);
+  h->timing.ops = res->ops;
+  h->timing.score_launches = res->score_launches;
+  h->timing.total_launches = res->launches;
+  h->timing.sub_batches = (uint32_t)res->n_subs;
+  h->timing.plan_uploaded = res->plan_uploaded;
+  if (h->opts.profile && res->ev.size() >= 4 * res->n_subs + 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, res->ev[0], res->ev[1]) == cudaSuccess) h->timing.total_ms = ms;
+    for (size_t k = 0; k < res->n_subs; ++k) {
+      if (cudaEventElapsedTime(&ms, res->ev[2 + 4 * k], res->ev[3 + 4 * k]) == cudaSuccess) h->timing.score_ms += ms;
+      if (cudaEventElapsedTime(&ms, res->ev[3 + 4 * k], res->ev[4 + 4 * k]) == cudaSuccess) h->timing.runner_up_ms += ms;
+      if (cudaEventElapsedTime(&ms, res->ev[4 + 4 * k], res->ev[5 + 4 * k]) == cudaSuccess) h->timing.decide_ms += ms;
+    }
+    cudaGetLastError();
+    h->timing.candidates = res->counters[1];
+  }
+  return SMB_OK;
+}
+
+static int begin_keys(smb_handle* h, std::vector<uint64_t>&& keys, size_t npairs, smb_result** out) {
+  *out = nullptr;
+  if (h->inflight) return fail(h, SMB_EINVAL, "a match call is already in flight on this handle (smb_result_wait it first)");
+  if (npairs > 0x7FFFFFFFull) return fail(h, SMB_EINVAL, "too many pairs in one call");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  smb_result* res = acquire_result(h);
+  if (!res) return fail(h, SMB_ENOMEM, "out of host memory");
+  res->keys = std::move(keys);
+  res->npairs = npairs;
+  res->total = 0;
+  res->pending = false;
+  if (npairs == 0) {
+    *out = res;
+    return SMB_OK;
+  }
+  int rc = enqueue_match(h, res, /*use_log=*/true, /*matches_want=*/0);
+  if (rc != SMB_OK) {
+    cudaStreamSynchronize(h->stream);
+    h->result_pool.push_back(res);
+    return rc;
+  }
+  res->pending = true;
+  h->inflight = res;
   *out = res;
   return SMB_OK;
 }
 
-static int match_keys(smb_handle* h, const uint64_t* keys, size_t npairs, smb_result** out) {
-  bool overflowed = false;
-  int rc = match_keys_impl(h, keys, npairs, out, /*use_log=*/true, &overflowed);
-  if (rc == SMB_OK && overflowed) rc = match_keys_impl(h, keys, npairs, out, /*use_log=*/false, &overflowed);  // exact, slower
+int smb_result_wait(smb_handle* h, smb_result* r) {
+  if (!h || !r) return SMB_EINVAL;
+  if (!r->pending) return SMB_OK;
+  if (h->inflight != r) return fail(h, SMB_EINVAL, "result does not belong to the call in flight on this handle");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  const int rc = finish_match(h, r);
+  r->pending = false;
+  h->inflight = nullptr;
+  flush_pending_free(h);
+  if (rc != SMB_OK) r->npairs = 0;  // nothing valid to read
   return rc;
 }
 
-int smb_match_pairs(smb_handle* h, const uint32_t* pairs, size_t npairs, smb_result** out) {
+int smb_match_pairs_begin(smb_handle* h, const uint32_t* pairs, size_t npairs, smb_result** out) {
   if (!h) return SMB_EINVAL;
   if (!out) return fail(h, SMB_EINVAL, "out pointer is null");
   if (npairs && !pairs) return fail(h, SMB_EINVAL, "pairs pointer is null");
   std::vector<uint64_t> keys(2 * npairs);
   for (size_t k = 0; k < 2 * npairs; ++k) keys[k] = pairs[k];
-  return match_keys(h, keys.data(), npairs, out);
+  return begin_keys(h, std::move(keys), npairs, out);
 }
 
-size_t smb_result_num_pairs(const smb_result* r) { return r ? r->pair_out.size() : 0; }
+int smb_match_pairs(smb_handle* h, const uint32_t* pairs, size_t npairs, smb_result** out) {
+  int rc = smb_match_pairs_begin(h, pairs, npairs, out);
+  if (rc != SMB_OK) return rc;
+  rc = smb_result_wait(h, *out);
+  if (rc != SMB_OK) {
+    smb_result_release(h, *out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+size_t smb_result_num_pairs(const smb_result* r) { return r && !r->pending ? r->npairs : 0; }
 
 const smb_match* smb_result_matches(const smb_result* r, size_t i, size_t* count) {
-  if (!r || i >= r->pair_out.size()) {
+  if (!r || r->pending || i >= r->npairs) {
     if (count) *count = 0;
     return nullptr;
   }
@@ -984,15 +1053,16 @@ const smb_match* smb_result_matches(const smb_result* r, size_t i, size_t* count
   return r->matches ? r->matches + r->pair_out[i].start : nullptr;
 }
 
-size_t smb_result_total_matches(const smb_result* r) { return r ? r->total : 0; }
+size_t smb_result_total_matches(const smb_result* r) { return r && !r->pending ? r->total : 0; }
 
 void smb_result_release(smb_handle* h, smb_result* r) {
   if (!r) return;
   if (h) {
+    if (r->pending) smb_result_wait(h, r);  // never recycle buffers the device may still write
+    r->npairs = 0;
     h->result_pool.push_back(r);
   } else {
-    if (r->matches) cudaFreeHost(r->matches);
-    delete r;
+    destroy_result(r);
   }
 }
 
@@ -1007,8 +1077,14 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
   if (rc == SMB_OK) rc = put_image_impl(h, k2, desc2, n2, kDim, cudaMemcpyHostToDevice);
   smb_result* res = nullptr;
   if (rc == SMB_OK) {
-    const uint64_t keys[2] = {k1, k2};
-    rc = match_keys(h, keys, 1, &res);
+    rc = begin_keys(h, std::vector<uint64_t>{k1, k2}, 1, &res);
+    if (rc == SMB_OK) {
+      rc = smb_result_wait(h, res);
+      if (rc != SMB_OK) {
+        smb_result_release(h, res);
+        res = nullptr;
+      }
+    }
   }
   if (rc == SMB_OK) {
     size_t c = 0;
@@ -1021,8 +1097,7 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
     }
     smb_result_release(h, res);
   }
-  cudaStreamSynchronize(h->stream);
-  for (uint64_t k : {k1, k2}) {
+  for (uint64_t k : {k1, k2}) {  // the call above has completed: nothing reads these rows any more
     auto it = h->images.find(k);
     if (it != h->images.end()) {
       free_rows(h, it->second.row0, it->second.rows);
@@ -1038,6 +1113,20 @@ int smb_get_timing(const smb_handle* h, smb_timing* t) {
   return SMB_OK;
 }
 
+int smb_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return SMB_EINVAL;
+  *out = nullptr;
+  if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, SMB_ENOMEM, "cudaMallocHost of %zu bytes failed", bytes);
+  }
+  return SMB_OK;
+}
+
+void smb_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int smb_get_filter(const smb_handle* h, int32_t* min_score, int32_t* min_best) {
   if (!h) return SMB_EINVAL;
   if (min_score) *min_score = h->filter.min_score;
@@ -1046,6 +1135,14 @@ int smb_get_filter(const smb_handle* h, int32_t* min_score, int32_t* min_best) {
 }
 
 void* smb_stream(const smb_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int smb_stream_wait_uploads(smb_handle* h, void* stream) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  if (h->up_issued > h->up_synced)  // tickets complete in order: the newest one covers all
+    SMB_CUDA(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->up_ev[h->up_issued % smb_handle::kUpRing], 0));
+  return SMB_OK;
+}
 
 int smb_synchronize(smb_handle* h) {
   if (!h) return SMB_EINVAL;

@@ -18,6 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmb.so")
+TEST_LIB_PATH = os.path.join(_HERE, "libsmb_test.so")   # + the CUDA-core cross-check engine; loaded by tests only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "smb.h")
 
 SMB_OK, SMB_EINVAL, SMB_ECUDA, SMB_ENOMEM, SMB_ENODEVICE, SMB_ECAPACITY = 0, -1, -2, -3, -4, -5
@@ -38,8 +39,9 @@ class smb_options(ctypes.Structure):
 
 
 class smb_timing(ctypes.Structure):
-    _fields_ = [("total_ms", ctypes.c_float), ("score_ms", ctypes.c_float), ("decide_ms", ctypes.c_float),
-                ("score_launches", ctypes.c_uint32), ("total_launches", ctypes.c_uint32),
+    _fields_ = [("total_ms", ctypes.c_float), ("score_ms", ctypes.c_float), ("runner_up_ms", ctypes.c_float),
+                ("decide_ms", ctypes.c_float), ("score_launches", ctypes.c_uint32), ("total_launches", ctypes.c_uint32),
+                ("sub_batches", ctypes.c_uint32), ("plan_uploaded", ctypes.c_uint32),
                 ("candidates", ctypes.c_uint64), ("ops", ctypes.c_uint64)]
 
 
@@ -47,20 +49,20 @@ class smb_match(ctypes.Structure):
     _fields_ = [("idx1", ctypes.c_uint32), ("idx2", ctypes.c_uint32)]
 
 
-_lib = None
+_libs = {}
 
 
 def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     """dlopen libsmb.so and declare every prototype of include/smb.h.  Raises if the library is absent:
     the product path must fail loudly rather than fall back."""
-    global _lib
-    if _lib is not None and path is None:
-        return _lib
     p = path or os.environ.get("SMB_LIB") or LIB_PATH   # SMB_LIB: A/B a build variant (tools/bin/*.so) under the tests
+    p = os.path.abspath(p)
+    if p in _libs:
+        return _libs[p]
     if not os.path.exists(p):
         raise SmbError(SMB_ENODEVICE, f"{p} not built -- run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = ctypes.CDLL(p)
-    vp, u32p, szp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)
+    vp, szp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)
     L.smb_default_options.argtypes = [ctypes.POINTER(smb_options)]
     L.smb_default_options.restype = None
     L.smb_abi_version.restype = ctypes.c_int
@@ -81,6 +83,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_clear_images.argtypes = [vp]
     L.smb_image_device_ptr.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(vp), szp]
     L.smb_match_pairs.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.smb_match_pairs_begin.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.smb_result_wait.argtypes = [vp, vp]
     L.smb_result_num_pairs.argtypes = [vp]
     L.smb_result_num_pairs.restype = ctypes.c_size_t
     L.smb_result_matches.argtypes = [vp, ctypes.c_size_t, szp]
@@ -94,10 +98,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_get_filter.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     L.smb_stream.argtypes = [vp]
     L.smb_stream.restype = vp
+    L.smb_stream_wait_uploads.argtypes = [vp, vp]
     L.smb_synchronize.argtypes = [vp]
-    del u32p
-    if path is None:
-        _lib = L
+    L.smb_alloc_pinned.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.smb_free_pinned.argtypes = [vp]
+    L.smb_free_pinned.restype = None
+    if L.smb_abi_version() != 2:
+        raise SmbError(SMB_EINVAL, f"{p}: ABI version {L.smb_abi_version()}, this mirror is written for 2 -- rebuild")
+    _libs[p] = L
     return L
 
 
@@ -117,8 +125,10 @@ class SiftMatcher:
 
     def __init__(self, device: int = 0, max_ratio: float = 0.8, max_distance: float = 0.7, cross_check: bool = True,
                  max_num_matches: int = 32768, engine: str = "tcgen05", profile: bool = False):
-        self._L = load_library()
+        # the product library has one engine; the CUDA-core cross-check lives in the tests' build of the same sources
+        self._L = load_library(TEST_LIB_PATH if engine != "tcgen05" and not os.environ.get("SMB_LIB") else None)
         self._h = ctypes.c_void_p()
+        self._keepalive: list = []
         self._opts = smb_options(float(max_ratio), float(max_distance), int(bool(cross_check)), int(max_num_matches),
                                  _ENGINES[engine], int(bool(profile)))
         rc = self._L.smb_create(int(device), ctypes.byref(self._opts), ctypes.byref(self._h))
@@ -184,7 +194,9 @@ class SiftMatcher:
         real overlap) until ``synchronize()`` or until a match call naming these images has returned."""
         ds = [_desc(d) for d in descriptors]
         n = len(ds)
-        self._keepalive = getattr(self, "_keepalive", [])[-256:] + ds
+        if len(self._keepalive) > 4096:      # a caller that never synchronises: drain, then the references can go
+            self.synchronize()
+        self._keepalive += ds                # the copies read these buffers until the uploads have landed
         ids = np.asarray(list(image_ids), dtype=np.uint32)
         ptrs = (ctypes.c_void_p * n)(*[d.ctypes.data for d in ds])
         ns = (ctypes.c_size_t * n)(*[d.shape[0] for d in ds])
@@ -221,7 +233,8 @@ class SiftMatcher:
         self._check(self._L.smb_evict_image(self._h, int(image_id)))
 
     def clear_images(self) -> None:
-        self._check(self._L.smb_clear_images(self._h))
+        self._check(self._L.smb_clear_images(self._h))   # drains pending uploads
+        self._keepalive.clear()
 
     def image_device_ptr(self, image_id: int) -> Tuple[int, int]:
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
@@ -229,25 +242,26 @@ class SiftMatcher:
         return (p.value or 0), n.value
 
     # -- matching ------------------------------------------------------------------------------
-    def match_pairs(self, pairs, copy: bool = True) -> List[np.ndarray]:
-        """Match (image_id1, image_id2) pairs of cached images.  Returns one uint32 [m, 2] array per
-        pair: (idx1, idx2) in ascending idx1 -- the FeatureMatches of MatchSiftFeaturesCPU."""
+    def match_pairs_begin(self, pairs) -> "MatchResult":
+        """Queue the whole call on the GPU and return at once; ``.wait()`` blocks until the matches are in host
+        memory.  One call in flight per matcher."""
         pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
         res = ctypes.c_void_p()
-        self._check(self._L.smb_match_pairs(self._h, pr.ctypes.data, pr.shape[0], ctypes.byref(res)))
-        try:
-            out = []
-            cnt = ctypes.c_size_t()
-            for i in range(pr.shape[0]):
-                ptr = self._L.smb_result_matches(res, i, ctypes.byref(cnt))
-                if cnt.value == 0:
-                    out.append(np.empty((0, 2), dtype=np.uint32))
-                    continue
-                a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(cnt.value, 2))
-                out.append(a.copy() if copy else a)
-            return out
-        finally:
-            self._L.smb_result_release(self._h, res)
+        self._check(self._L.smb_match_pairs_begin(self._h, pr.ctypes.data, pr.shape[0], ctypes.byref(res)))
+        return MatchResult(self, res, pr.shape[0])
+
+    def match_pairs_result(self, pairs) -> "MatchResult":
+        """match_pairs, but the (completed) result object is handed out instead of copies of every list: the
+        benchmark keeps the last timed call's result and checks a sample of it afterwards."""
+        r = self.match_pairs_begin(pairs)
+        r.wait()
+        return r
+
+    def match_pairs(self, pairs) -> List[np.ndarray]:
+        """Match (image_id1, image_id2) pairs of cached images.  Returns one uint32 [m, 2] array per
+        pair: (idx1, idx2) in ascending idx1 -- the FeatureMatches of MatchSiftFeaturesCPU."""
+        with self.match_pairs_result(pairs) as r:
+            return [r.matches(i) for i in range(r.num_pairs)]
 
     def match_pairs_count(self, pairs) -> int:
         """Same work as match_pairs (results reach pinned host memory) but only the total is returned;
@@ -279,8 +293,62 @@ class SiftMatcher:
     def stream(self) -> int:
         return self._L.smb_stream(self._h) or 0
 
+    def stream_wait_uploads(self, stream: int) -> None:
+        """Make `stream` (a cudaStream_t handle) wait on the device for every upload queued so far."""
+        self._check(self._L.smb_stream_wait_uploads(self._h, ctypes.c_void_p(int(stream))))
+
     def synchronize(self) -> None:
         self._check(self._L.smb_synchronize(self._h))
+        self._keepalive.clear()
+
+
+class MatchResult:
+    """Owns one smb_result (pinned host memory the device wrote directly).  Arrays handed out are copies, so they
+    stay valid after ``release()`` hands the buffers back to the matcher's pool."""
+
+    def __init__(self, matcher: SiftMatcher, handle: ctypes.c_void_p, npairs: int):
+        self._m, self._r, self._n, self._waited = matcher, handle, npairs, False
+
+    def wait(self) -> "MatchResult":
+        if not self._waited:
+            self._m._check(self._m._L.smb_result_wait(self._m._h, self._r))
+            self._waited = True
+        return self
+
+    @property
+    def num_pairs(self) -> int:
+        return self._n
+
+    @property
+    def total(self) -> int:
+        self.wait()
+        return int(self._m._L.smb_result_total_matches(self._r))
+
+    def matches(self, i: int) -> np.ndarray:
+        self.wait()
+        cnt = ctypes.c_size_t()
+        ptr = self._m._L.smb_result_matches(self._r, int(i), ctypes.byref(cnt))
+        if cnt.value == 0:
+            return np.empty((0, 2), dtype=np.uint32)
+        a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(cnt.value, 2))
+        return a.copy()
+
+    def release(self) -> None:
+        if self._r is not None and self._m._h:
+            self._m._L.smb_result_release(self._m._h, self._r)
+        self._r = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def sequential_pairs(image_ids: Sequence[int], overlap: int) -> np.ndarray:

@@ -40,6 +40,9 @@ void smb_op_delete_kernel(smb_op_kernel* h) {
   delete h;
 }
 
+void smb_op_reset(smb_op_kernel* h) { h->k->reset(); }
+void smb_op_new_stream(smb_op_kernel* h) { h->k->new_stream(std::vector<scanner::u8>()); }
+
 // inputs: ncols x batch x stencil element pointers/sizes flattened in that order
 int smb_op_execute(smb_op_kernel* h, size_t ncols, size_t batch, size_t stencil, const uint8_t* const* bufs, const size_t* sizes,
                    size_t nout) {

@@ -19,6 +19,11 @@ class BaseKernel {
  public:
   explicit BaseKernel(const KernelConfig&) {}
   virtual ~BaseKernel() {}
+  // Scanner calls reset() when the next rows are not contiguous with the previous ones, and new_stream() when
+  // the kernel instance is handed another table / job [ext]: whatever a kernel cached about earlier rows is
+  // stale from then on.
+  virtual void reset() {}
+  virtual void new_stream(const std::vector<u8>& /*args*/) {}
 };
 
 // sequential_matching.cc:27-33,103-108: execute(const StenciledBatchedElements&, BatchedElements&)

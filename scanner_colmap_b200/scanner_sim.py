@@ -38,6 +38,10 @@ def harness() -> ctypes.CDLL:
         L.smb_op_delete_kernel.argtypes = [vp]
         L.smb_op_delete_kernel.restype = None
         L.smb_op_execute.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, ctypes.c_size_t]
+        L.smb_op_reset.argtypes = [vp]
+        L.smb_op_reset.restype = None
+        L.smb_op_new_stream.argtypes = [vp]
+        L.smb_op_new_stream.restype = None
         L.smb_op_output_count.argtypes = [vp, ctypes.c_size_t]
         L.smb_op_output_count.restype = ctypes.c_size_t
         L.smb_op_output.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
@@ -63,21 +67,42 @@ def op_description(name: str = "SequentialMatchingCPU") -> str:
     return buf.value.decode()
 
 
-def run_feature_matching(image_ids: Sequence[int], keypoints: Sequence[np.ndarray], descriptors: Sequence[np.ndarray],
-                         overlap: int = 10, packet_size: int = 25, args: bytes = b"") -> Tuple[List[List[int]], List[list]]:
-    """``feature_matching.py --overlap W --packet_size P`` on an in-memory extraction table.
-    Returns (pair_image_ids per row, decoded two_view_geometries per row)."""
-    L = harness()
-    n = len(image_ids)
-    cols = [[wire.encode_image_id(i) for i in image_ids],
-            [wire.encode_keypoints(k) for k in keypoints],
-            [wire.encode_descriptors(d) for d in descriptors]]
-    k = L.smb_op_new_kernel(b"SequentialMatchingCPU", args, len(args))
-    if not k:
-        raise RuntimeError("kernel creation failed")
-    out_ids: List[List[int]] = []
-    out_tvg: List[list] = []
-    try:
+class OpKernel:
+    """One kernel instance of the op, as Scanner keeps one per pipeline instance: it outlives a single table (Scanner
+    reuses instances across tasks and jobs and announces the change with reset() / new_stream())."""
+
+    def __init__(self, args: bytes = b"", name: str = "SequentialMatchingCPU"):
+        self._L = harness()
+        self._k = self._L.smb_op_new_kernel(name.encode(), args, len(args))
+        if not self._k:
+            raise RuntimeError("kernel creation failed")
+
+    def close(self):
+        if self._k:
+            self._L.smb_op_delete_kernel(self._k)
+            self._k = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        self._L.smb_op_reset(self._k)
+
+    def new_stream(self):
+        self._L.smb_op_new_stream(self._k)
+
+    def run_table(self, image_ids: Sequence[int], keypoints: Sequence[np.ndarray], descriptors: Sequence[np.ndarray],
+                  overlap: int = 10, packet_size: int = 25, decode: bool = True, encoded=None):
+        """``feature_matching.py --overlap W --packet_size P`` over an in-memory extraction table.  Returns
+        (pair_image_ids per row, two_view_geometries per row) -- decoded, or with ``decode=False`` the raw
+        serialized rows (the op-level benchmark keeps Python decoding out of its timed region)."""
+        L, k = self._L, self._k
+        n = len(image_ids)
+        cols = encoded or encode_table(image_ids, keypoints, descriptors)
+        out_ids, out_tvg = [], []
         for start in range(0, n, packet_size):
             rows = list(range(start, min(start + packet_size, n)))
             batch = len(rows)
@@ -98,7 +123,19 @@ def run_feature_matching(image_ids: Sequence[int], keypoints: Sequence[np.ndarra
                 for i in range(batch):
                     sz = ctypes.c_size_t()
                     p = L.smb_op_output(k, col, i, ctypes.byref(sz))
-                    sink.append(dec(ctypes.string_at(p, sz.value)))
-    finally:
-        L.smb_op_delete_kernel(k)
-    return out_ids, out_tvg
+                    sink.append(dec(ctypes.string_at(p, sz.value)) if decode else sz.value)
+        return out_ids, out_tvg
+
+
+def encode_table(image_ids, keypoints, descriptors):
+    """The three input columns of the ``extraction`` table as serialized elements (io.cc formats)."""
+    return [[wire.encode_image_id(i) for i in image_ids],
+            [wire.encode_keypoints(k) for k in keypoints],
+            [wire.encode_descriptors(d) for d in descriptors]]
+
+
+def run_feature_matching(image_ids: Sequence[int], keypoints: Sequence[np.ndarray], descriptors: Sequence[np.ndarray],
+                         overlap: int = 10, packet_size: int = 25, args: bytes = b"") -> Tuple[List[List[int]], List[list]]:
+    """A fresh kernel instance over one table (what one ``python3 feature_matching.py`` run amounts to)."""
+    with OpKernel(args) as k:
+        return k.run_table(image_ids, keypoints, descriptors, overlap=overlap, packet_size=packet_size)

@@ -24,7 +24,7 @@ def test_header_symbols_exported(built):
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"libsmb.so does not export {n}"
-    assert L.smb_abi_version() == 1
+    assert L.smb_abi_version() == 2
 
 
 def test_no_torch_types_in_abi():
@@ -50,6 +50,21 @@ def test_sass_is_blackwell_native(built):
     assert "sm_100a" in sass
     for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "VIMNMX3"):
         assert mnemonic in sass, mnemonic
+
+
+def test_product_library_has_one_engine(built):
+    """north_star: no multi-backend dispatch.  The CUDA-core cross-check engine exists only in the tests' build
+    (libsmb_test.so, -DSMB_TEST_ENGINES); the product library must not contain it."""
+    def kernels(path):
+        out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True)
+        if out.returncode != 0:
+            pytest.skip("cuobjdump unavailable")
+        return set(re.findall(r"Function : (\S+)", out.stdout))
+    prod, test = kernels(matcher.LIB_PATH), kernels(matcher.TEST_LIB_PATH)
+    assert not any("dp4a" in k for k in prod), prod
+    assert any("dp4a" in k for k in test)
+    assert any("score_tcgen05_kernel" in k for k in prod)
+    assert prod < test          # same kernels otherwise
 
 
 def test_fails_loudly_without_gpu(built):

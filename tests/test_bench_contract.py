@@ -38,3 +38,23 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     assert out.returncode != 0
     assert "no CUDA device" in (out.stderr + out.stdout)
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]   # and prints no number
+
+
+def test_reference_arm_under_torchrun_uses_every_core_and_only_rank0_works(built):
+    """The driver launches the reference arm like the product arm (torchrun for N > 1).  torch.distributed.run
+    exports OMP_NUM_THREADS=1 to its workers: the CPU matcher must still use all host cores (round 1's reference
+    arm ran single-threaded there and hit the driver's time limit), and ranks other than 0 exit 0 without work."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))     # not 1

@@ -78,3 +78,51 @@ def test_duplicate_ids_and_empty_images(oracle):
             w = oracle.match(descs[r], base[pid])
             w = w if len(w) >= 15 else np.empty((0, 2), np.uint32)
             assert np.array_equal(g.inlier_matches, w)
+
+
+def test_one_kernel_instance_two_tables_with_colliding_ids(oracle):
+    """Image ids restart at 0 in every prepare_image kernel instance (prepare_image.cc:12), so they collide across
+    tables and jobs, and Scanner reuses a kernel instance across them.  The op's descriptor cache must never serve
+    table A's descriptors to table B: with new_stream() announced, and -- belt and braces -- without it (every cache
+    hit is validated against the row's size and content signature)."""
+    n, overlap = 8, 4
+    ids = list(range(n))
+    table_a = [synth.make_image(100 + i, 600 + 10 * i, track_step=24) for i in ids]
+    table_b = [synth.make_image(200 + i, 600 + 10 * i, track_step=24) for i in ids]      # same ids, same sizes, other bytes
+    kps = [np.zeros((len(d), 6), np.float32) for d in table_a]
+    want_a = _expected_rows(oracle, ids, table_a, overlap)
+    want_b = _expected_rows(oracle, ids, table_b, overlap)
+
+    def check(got, want):
+        got_ids, got_tvg = got
+        for r, (partners, tv) in enumerate(want):
+            assert got_ids[r] == partners
+            for g, w in zip(got_tvg[r], tv):
+                assert np.array_equal(g.inlier_matches, w), f"row {r}"
+
+    with scanner_sim.OpKernel() as k:
+        check(k.run_table(ids, kps, table_a, overlap=overlap, packet_size=3), want_a)
+        check(k.run_table(ids, kps, table_b, overlap=overlap, packet_size=3), want_b)     # no reset announced
+        k.new_stream()
+        check(k.run_table(ids, kps, table_a, overlap=overlap, packet_size=8), want_a)
+        k.reset()
+        check(k.run_table(ids, kps, table_b, overlap=overlap, packet_size=2), want_b)
+
+
+def test_kernel_instances_share_one_gpu_context(oracle):
+    """Scanner makes one CPU kernel instance per pipeline instance; they must not each own a matcher (pool, log,
+    accumulators, persistent kernels).  Two instances with different kernel args interleave on the shared handle."""
+    ids = [11, 12, 13, 14]
+    descs = [synth.make_image(i, 500, track_step=16, noise=0.2) for i in ids]
+    kps = [np.zeros((500, 6), np.float32)] * 4
+    args2 = wire.encode_matching_args(max_ratio=0.95, max_distance=1.0, cross_check=False, min_num_inliers=1)
+    want1 = _expected_rows(oracle, ids, descs, 3)
+    want2 = _expected_rows(oracle, ids, descs, 3, min_num_inliers=1, max_ratio=0.95, max_distance=1.0, cross_check=False)
+    with scanner_sim.OpKernel() as k1, scanner_sim.OpKernel(args2) as k2:
+        for _ in range(2):
+            for k, want in ((k1, want1), (k2, want2)):
+                got_ids, got_tvg = k.run_table(ids, kps, descs, overlap=3, packet_size=2)
+                for r, (partners, tv) in enumerate(want):
+                    assert got_ids[r] == partners
+                    for g, w in zip(got_tvg[r], tv):
+                        assert np.array_equal(g.inlier_matches, w)

@@ -43,6 +43,33 @@ def test_uniform_partition_is_near_equal_and_ragged_is_cost_balanced():
     assert max(per) / np.mean(per) < 1.05
 
 
+@pytest.mark.parametrize("n,world", [(200, 8), (200, 4), (200, 2), (200, 1), (24, 3), (7, 8), (2, 4)])
+def test_exhaustive_plan_tiles_the_triangle(n, world):
+    """BASELINE configs[4]: all pairs i < j, 2-D tiled over image blocks; every pair exactly once, send/recv lists
+    agree, every needed row is owned or received."""
+    sizes = [16384] * n
+    plans = [sharding.plan_exhaustive(sizes, world, r) for r in range(world)]
+    seen = [tuple(x) for p in plans for x in p.pairs.tolist()]
+    assert len(seen) == len(set(seen)) == n * (n - 1) // 2 and all(a < b for a, b in seen)
+    sends = {(row, r, dst) for r, p in enumerate(plans) for row, dst in p.send}
+    recvs = {(row, src, r) for r, p in enumerate(plans) for row, src in p.recv}
+    assert sends == recvs
+    owned = [set(range(*p.own)) for p in plans]
+    assert sorted(x for o in owned for x in o) == list(range(n))           # every image has exactly one owner
+    for r, p in enumerate(plans):
+        needed = {int(x) for x in p.pairs.reshape(-1)}
+        assert needed <= owned[r] | {row for row, _ in p.recv}
+        assert set(p.need) >= needed
+
+
+def test_exhaustive_plan_is_balanced_and_holds_half_the_descriptors_on_8_gpus():
+    p = sharding.plan_exhaustive([16384] * 200, 8, 0)
+    assert p.imbalance <= 1.03 and p.resident_fraction <= 0.51 and len(p.blocks) == 4
+    sizes = synth.ragged_sizes(300).tolist()
+    q = sharding.plan_exhaustive(sizes, 8, 3)
+    assert q.imbalance <= 1.03 and q.resident_fraction < 0.8
+
+
 def _worker(rank, world, port, n, overlap, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -60,6 +87,14 @@ def _worker(rank, world, port, n, overlap, q):
                                              lambda rows: torch.cat([own[r].reshape(-1) for r in rows]),
                                              lambda src, nbytes: torch.empty(nbytes, dtype=torch.uint8))
         ok = ok and sorted(got2) == sorted(got) and all(torch.equal(got2[row], got[row]) for row in got)
+        # exhaustive plan: rows come from the owners of the blocks this rank's tiles touch
+        pe = sharding.plan_exhaustive(sizes, world, rank)
+        mine = {i: torch.from_numpy(synth.make_image(i, sizes[i], track_step=4)) for i in range(*pe.own)}
+        got3 = sharding.exchange_halo_packed(pe, lambda row: sizes[row] * 128,
+                                             lambda rows: torch.cat([mine[r].reshape(-1) for r in rows]),
+                                             lambda src, nbytes: torch.empty(nbytes, dtype=torch.uint8))
+        ok = ok and sorted(got3) == [row for row, _ in pe.recv] and all(
+            np.array_equal(got3[row].numpy().reshape(-1, 128), synth.make_image(row, sizes[row], track_step=4)) for row in got3)
         q.put((rank, ok, len(p.recv), len(p.send), len(p.pairs)))
     finally:
         dist.destroy_process_group()

@@ -4,7 +4,7 @@ import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from scanner_colmap_b200 import matcher, synth, sequential_pairs
-matcher._lib = matcher.load_library(os.path.join(ROOT, "tools", "bin", os.environ.get("SMB_TRACE_LIB", "libsmb_trace.so")))
+os.environ['SMB_LIB'] = os.path.join(ROOT, "tools", "bin", os.environ.get("SMB_TRACE_LIB", "libsmb_trace.so"))
 n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 ids = list(range(n_img)); imgs = synth.make_images(n_img, 8192); pairs = sequential_pairs(ids, 10)
 m = matcher.SiftMatcher(profile=True)

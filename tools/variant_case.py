@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from scanner_colmap_b200 import matcher, synth, sequential_pairs
 lib = sys.argv[1]
-matcher._lib = matcher.load_library(lib if os.path.isabs(lib) else os.path.join(ROOT, lib))
+os.environ['SMB_LIB'] = lib if os.path.isabs(lib) else os.path.join(ROOT, lib)
 n_img = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ids = list(range(n_img)); imgs = synth.make_images(n_img, 8192); pairs = sequential_pairs(ids, 10)
