@@ -47,6 +47,11 @@ struct Filter {
   int32_t min_score;  // smallest score that can change any decision, clamped to >= 1
 };
 
+struct Sub {  // one internal batch of a match call: pairs [first, last), its work items and accumulator slots
+  size_t first, last, item0, items, acc;
+  uint64_t split_ticket, wait_ticket;
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -162,6 +167,15 @@ struct smb_handle {
   std::vector<PairMeta> plan_pairs;  // the plan being built; uploaded only if it differs from h_pairs / h_items
   std::vector<WorkItem> plan_items;
   size_t dev_plan_pairs = 0, dev_plan_items = 0;  // extent of the valid device copy (0 = none)
+  // Steady state (the same pair list over an unchanged pool layout, e.g. every step of a resident window, or a
+  // window whose halo images are refreshed in place): the whole plan of the previous call is reused, so a call costs
+  // the host a 14 KB compare and five launches instead of ~0.25 ms of planning with the GPU idle.
+  uint64_t layout_epoch = 1;          // bumped whenever an image appears, disappears or moves
+  uint64_t plan_epoch = 0;            // layout the stored plan was made for (0 = no stored plan)
+  std::vector<uint64_t> plan_keys;
+  std::vector<Sub> plan_subs;
+  size_t plan_out_cap = 0, plan_max_acc = 0, plan_acc_budget = 0;
+  uint64_t plan_ops = 0;
 
   std::vector<smb_result*> result_pool;
   smb_result* inflight = nullptr;        // begun, not yet waited for
@@ -310,6 +324,7 @@ int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
     SMB_CUDA(h, cudaFree(h->pool));
   }
   h->dev_plan_pairs = h->dev_plan_items = 0;  // (the plan holds pool rows, which are unchanged, but be safe)
+  ++h->layout_epoch;
   const uint32_t old_rows = h->pool_rows;
   h->pool = np;
   h->pool_rows = (uint32_t)want;
@@ -380,10 +395,25 @@ int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_
   if (n && !src) return fail(h, SMB_EINVAL, "descriptor pointer is null");
   if (n > 0x7FFFFFFFu) return fail(h, SMB_EINVAL, "too many descriptors in one image: %zu", n);
   auto old = h->images.find(key);
+  if (old != h->images.end() && old->second.n == n && !h->inflight) {
+    // Same id, same size, nothing reading the pool: refresh the rows in place.  The layout (and with it any plan
+    // built on it) stays valid; only the upload ticket changes.  Copies are ordered per stream, so only a pending
+    // upload on the OTHER stream into these rows has to land first.
+    ImageEntry& e = old->second;
+    if (e.up_seq > h->up_synced && stream != h->stream_up) {
+      poll_uploads(h);
+      if (e.up_seq > h->up_synced)
+        if (int rc = drain_uploads(h)) return rc;
+    }
+    if (n) SMB_CUDA(h, cudaMemcpyAsync(h->pool + (size_t)e.row0 * kDim, src, n * kDim, kind, stream));
+    e.up_seq = up_seq;
+    return SMB_OK;
+  }
   if (old != h->images.end()) {
     if (int rc = retire_rows(h, old->second)) return rc;
     h->images.erase(old);
   }
+  ++h->layout_epoch;
   ImageEntry e;
   e.n = (uint32_t)n;
   e.rows = (uint32_t)((n + kRowPad - 1) / kRowPad * kRowPad);
@@ -670,6 +700,7 @@ int smb_evict_image(smb_handle* h, uint32_t image_id) {
   SMB_CUDA(h, cudaSetDevice(h->device));
   if (int rc = retire_rows(h, it->second)) return rc;  // no device synchronisation (see retire_rows)
   h->images.erase(it);
+  ++h->layout_epoch;
   return SMB_OK;
 }
 
@@ -681,6 +712,7 @@ int smb_clear_images(smb_handle* h) {
   h->images.clear();
   h->free_list.clear();
   if (h->pool_rows) h->free_list.emplace(0u, h->pool_rows);
+  ++h->layout_epoch;
   return SMB_OK;
 }
 
@@ -719,16 +751,31 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   poll_uploads(h);  // uploads that have landed since the last look need no waiting (and no sub-batch of their own)
 
   // ---- plan: metas, work items, sub-batches
-  struct Sub { size_t first, last, item0, items, acc; uint64_t split_ticket, wait_ticket; };
   std::vector<Sub> subs;
   std::vector<PairMeta>& pm = h->plan_pairs;
   std::vector<WorkItem>& wi = h->plan_items;
-  pm.resize(npairs);
-  wi.clear();
   const size_t sub_budget = h->acc_budget;
   size_t out_cap = 0, max_acc = 0;
   uint64_t ops = 0;
   auto is_host_ticket = [&](uint64_t t) { return t > h->up_synced && !h->up_fast[t % smb_handle::kUpRing]; };
+  bool pending_host = false;
+  for (uint64_t t = h->up_synced + 1; t <= h->up_issued; ++t) pending_host = pending_host || !h->up_fast[t % smb_handle::kUpRing];
+  const bool reuse = h->plan_epoch == h->layout_epoch && !pending_host && h->plan_acc_budget == sub_budget &&
+                     h->plan_keys.size() == 2 * npairs && h->dev_plan_pairs == npairs && h->dev_plan_items == wi.size() &&
+                     std::memcmp(h->plan_keys.data(), keys, 2 * npairs * sizeof(uint64_t)) == 0;
+  if (reuse) {
+    subs = h->plan_subs;
+    out_cap = h->plan_out_cap;
+    max_acc = h->plan_max_acc;
+    ops = h->plan_ops;
+    // images refreshed in place since the plan was made (the halo): their tickets complete in order, so the first
+    // sub-batch waiting for the newest pending one covers them all
+    for (Sub& sb : subs) sb.wait_ticket = 0;
+    if (h->up_issued > h->up_synced) subs[0].wait_ticket = h->up_issued;
+  } else {
+  h->plan_epoch = 0;
+  pm.resize(npairs);
+  wi.clear();
   // Planned order: with host uploads still in flight, pairs are taken in the order their images land (stable), so an
   // early pair listed after a late one does not wait for the late one's upload.  order[q] = caller index.
   std::vector<uint32_t>& order = h->plan_order;
@@ -811,6 +858,16 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
     }
   }
   if (out_cap > 0xFFFFFF00ull) return fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call");
+  if (!pending_host && order.empty()) {  // reusable as long as the layout and the pair list stay the same
+    h->plan_keys.assign(keys, keys + 2 * npairs);
+    h->plan_subs = subs;
+    h->plan_out_cap = out_cap;
+    h->plan_max_acc = max_acc;
+    h->plan_ops = ops;
+    h->plan_acc_budget = sub_budget;
+    h->plan_epoch = h->layout_epoch;   // (the device copy of the plan is made below)
+  }
+  }  // !reuse
   res->worst_case = out_cap;
   const size_t n_items_total = wi.size();
   const size_t acc_region = (max_acc + 15) / 16 * 16;
@@ -861,9 +918,10 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   // ---- plan upload, skipped when the device already holds exactly this plan (steady state: same pairs, same rows).
   // The device reads the pinned plan directly (UVA): a cudaMemcpyAsync would queue behind whatever descriptor uploads
   // are already in the host->device copy engine's FIFO and stall the score kernel it feeds.
-  const bool same_plan = h->dev_plan_pairs == npairs && h->dev_plan_items == n_items_total &&
-                         std::memcmp(h->h_pairs.p, pm.data(), npairs * sizeof(PairMeta)) == 0 &&
-                         (n_items_total == 0 || std::memcmp(h->h_items.p, wi.data(), n_items_total * sizeof(WorkItem)) == 0);
+  const bool same_plan = reuse || (h->dev_plan_pairs == npairs && h->dev_plan_items == n_items_total &&
+                                   std::memcmp(h->h_pairs.p, pm.data(), npairs * sizeof(PairMeta)) == 0 &&
+                                   (n_items_total == 0 ||
+                                    std::memcmp(h->h_items.p, wi.data(), n_items_total * sizeof(WorkItem)) == 0));
   if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[0], st));
   SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, smb_handle::kNumCounters * sizeof(unsigned long long), st));
   if (!same_plan) {
@@ -1102,6 +1160,7 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
     if (it != h->images.end()) {
       free_rows(h, it->second.row0, it->second.rows);
       h->images.erase(it);
+      ++h->layout_epoch;
     }
   }
   return rc;

@@ -405,8 +405,7 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     std::memcpy(out.inlier_matches.data(), g.inlier_matches.data(), 8 * g.inlier_matches.size());
 #else
     (void)kp1; (void)kp2;
-    out.inlier_matches.resize(m);
-    if (m) std::memcpy(out.inlier_matches.data(), matches, m * sizeof(FeatureMatch));
+    out.inlier_matches.assign(reinterpret_cast<const FeatureMatch*>(matches), reinterpret_cast<const FeatureMatch*>(matches) + m);
 #endif
     return out;
   }

@@ -94,14 +94,10 @@ def exchange_halo(p: ShardPlan, get_tensor: Callable[[int], "object"], make_recv
     return out
 
 
-def exchange_halo_packed(p: ShardPlan, row_bytes: Callable[[int], int], get_send: Callable[[List[int]], "object"],
-                         make_recv: Callable[[int, int], "object"], group=None) -> dict:
-    """Same exchange with ONE message per peer instead of one per image (queuing 18 point-to-point operations
-    through torch.distributed costs 0.2-0.45 ms of host time per step on 8 GPUs).  ``get_send(rows)`` returns a
-    1-D uint8 tensor holding those rows back to back (a zero-copy view when they are adjacent in the descriptor
-    pool, a packed copy otherwise); ``make_recv(src, nbytes)`` returns the 1-D uint8 receive buffer for everything
-    coming from rank ``src``.  Returns {row: 1-D view of that row's bytes inside its receive buffer}.  Both sides
-    derive the message sizes from the plan alone, so they always agree."""
+def halo_ops_packed(p, row_bytes: Callable[[int], int], get_send: Callable[[List[int]], "object"],
+                    make_recv: Callable[[int, int], "object"], group=None):
+    """The point-to-point operations of ``exchange_halo_packed`` without issuing them: (ops, {row: view}).  A caller
+    whose send views and receive buffers do not move can build them once and re-issue them every step."""
     import torch.distributed as dist
     by_dst, by_src = {}, {}
     for row, dst in p.send:
@@ -119,6 +115,19 @@ def exchange_halo_packed(p: ShardPlan, row_bytes: Callable[[int], int], get_send
             out[r] = buf[off:off + row_bytes(r)]
             off += row_bytes(r)
         ops.append(dist.P2POp(dist.irecv, buf, src, group=group))
+    return ops, out
+
+
+def exchange_halo_packed(p: ShardPlan, row_bytes: Callable[[int], int], get_send: Callable[[List[int]], "object"],
+                         make_recv: Callable[[int, int], "object"], group=None) -> dict:
+    """Same exchange with ONE message per peer instead of one per image (queuing 18 point-to-point operations
+    through torch.distributed costs 0.2-0.45 ms of host time per step on 8 GPUs).  ``get_send(rows)`` returns a
+    1-D uint8 tensor holding those rows back to back (a zero-copy view when they are adjacent in the descriptor
+    pool, a packed copy otherwise); ``make_recv(src, nbytes)`` returns the 1-D uint8 receive buffer for everything
+    coming from rank ``src``.  Returns {row: 1-D view of that row's bytes inside its receive buffer}.  Both sides
+    derive the message sizes from the plan alone, so they always agree."""
+    import torch.distributed as dist
+    ops, out = halo_ops_packed(p, row_bytes, get_send, make_recv, group)
     if ops:
         for r in dist.batch_isend_irecv(ops):
             r.wait()

@@ -296,9 +296,22 @@ def test_begin_wait_and_plan_reuse(oracle):
         with m.match_pairs_result(pairs) as r2:
             assert m.timing()["plan_uploaded"] == 0 and m.timing()["total_launches"] == 3   # score, runner-up, decide
             assert all(np.array_equal(r2.matches(k), want[k]) for k in range(len(pairs)))
-        m.put_image(3, imgs[3])                       # same bytes, but the rows may move: the plan is compared, not assumed
+        # an image of the same size is refreshed IN PLACE (the halo of every multi-GPU step): the stored plan stays valid,
+        # the new bytes must be what the next call sees
+        imgs2 = list(imgs)
+        imgs2[3] = synth.make_image(333, imgs[3].shape[0], track_step=64)
+        m.put_image(3, imgs2[3])
+        want2, _ = oracle.match_many(imgs2, [(int(a), int(b)) for a, b in pairs])
         with m.match_pairs_result(pairs) as r3:
-            assert all(np.array_equal(r3.matches(k), want[k]) for k in range(len(pairs)))
+            assert m.timing()["plan_uploaded"] == 0
+            assert all(np.array_equal(r3.matches(k), want2[k]) for k in range(len(pairs)))
+        m.put_image(3, imgs[3][:-1])                  # another size: rows move, the plan is rebuilt
+        imgs2[3] = imgs[3][:-1]
+        want3, _ = oracle.match_many(imgs2, [(int(a), int(b)) for a, b in pairs])
+        with m.match_pairs_result(pairs) as r4:
+            assert m.timing()["plan_uploaded"] == 1
+            assert all(np.array_equal(r4.matches(k), want3[k]) for k in range(len(pairs)))
+        m.put_image(3, imgs[3])
         got = m.match_pairs(np.array([[51, 0]], dtype=np.uint32))[0]
         assert np.array_equal(got, oracle.match(extra[1], imgs[0]))
         m.stream_wait_uploads(m.stream)
