@@ -158,6 +158,41 @@ int smb_match_descriptors(smb_handle* h, const uint8_t* desc1, size_t n1, const 
 
 int smb_get_timing(const smb_handle* h, smb_timing* t);
 
+/* ---- Two-view geometry verification on the GPU (the step after the matcher in the reference op:
+ * verifyTwoViewGeometry -> colmap::TwoViewGeometry::Estimate, sequential_matching.cc:84-101,157-178, which with the
+ * reference's dummy cameras is the uncalibrated F / H LORANSAC path).  Statistical contract, not bit parity: COLMAP
+ * samples from a thread-local PRNG (DESIGN.md "Two-view geometry"). */
+typedef struct smb_tvg_options {
+  int32_t min_num_inliers; /* colmap.proto:41 default 15 */
+  int32_t min_num_trials;  /* colmap.proto:32 default 30 */
+  int32_t max_num_trials;  /* colmap.proto:33 default 10000 */
+  int32_t pad_;
+  double max_error;        /* colmap.proto:26 default 4.0 (pixels) */
+  double confidence;       /* colmap.proto:29 default 0.999 */
+  double min_inlier_ratio; /* colmap.proto:37 default 0.25 */
+  double max_h_inlier_ratio; /* COLMAP's TwoViewGeometry::Options default 0.8 (not in the reference's proto) */
+  uint64_t seed;
+} smb_tvg_options;
+void smb_default_tvg_options(smb_tvg_options* o);
+
+typedef struct smb_tvg {
+  int32_t config;           /* colmap::TwoViewGeometry::ConfigurationType: 1 DEGENERATE, 3 UNCALIBRATED, 6 PLANAR_OR_PANORAMIC */
+  int32_t num_inliers_f, num_inliers_h;
+  int32_t trials_f, trials_h;
+  uint32_t inlier_start, inlier_count; /* internal offsets; use smb_result_inliers */
+  uint32_t pad_;
+  double F[9], H[9];        /* row-major */
+} smb_tvg;
+
+/* Keypoint positions (x, y) of a cached image: `n` must equal its descriptor count; `xy` points at the first x,
+ * consecutive keypoints are `stride_bytes` apart (24 for colmap::FeatureKeypoint rows, io.cc:115-123; 8 for packed). */
+int smb_put_keypoints(smb_handle* h, uint32_t image_id, const float* xy, size_t n, size_t stride_bytes);
+/* Verify every pair of `r`, which must be the most recent completed match call of `h`, and whose images must all
+ * have keypoints.  Fills per pair a smb_tvg and the inlier matches (ascending idx1, pinned host memory). */
+int smb_result_verify(smb_handle* h, smb_result* r, const smb_tvg_options* opts);
+int smb_result_tvg(const smb_result* r, size_t i, smb_tvg* out);
+const smb_match* smb_result_inliers(const smb_result* r, size_t i, size_t* count);
+
 /* Page-locked host memory for callers that do not link the CUDA runtime themselves (the op stages Scanner's
  * pageable descriptor rows through such a buffer so that smb_put_images_async really is asynchronous). */
 int smb_alloc_pinned(size_t bytes, void** out);

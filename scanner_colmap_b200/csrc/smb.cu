@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "verify.cuh"
 
 namespace {
 
@@ -40,6 +41,7 @@ struct ImageEntry {
   uint32_t n;      // descriptor count
   uint32_t rows;   // reserved pool rows (multiple of kRowPad)
   uint64_t up_seq; // 0 = resident; otherwise the upload ticket (smb_put_images_async) that fills it
+  bool has_kp = false;  // keypoint positions present (smb_put_keypoints)
 };
 
 struct Filter {
@@ -109,6 +111,11 @@ struct smb_result {
   size_t matches_limit = 0;      // entries the device may write in the current attempt (<= matches_cap)
   unsigned long long* counters = nullptr;  // pinned [kNumCounters]: the device counters as of the end of the call
   size_t total = 0;
+  smb_tvg* tvg = nullptr;        // pinned [tvg_cap], written by verify_kernel (smb_result_verify)
+  size_t tvg_cap = 0;
+  smb_match* inliers = nullptr;  // pinned [inliers_cap], same offsets as matches
+  size_t inliers_cap = 0;
+  bool verified = false;
   // between smb_match_pairs_begin and smb_result_wait
   bool pending = false;
   bool used_log = false;
@@ -141,6 +148,10 @@ struct smb_handle {
                                       // microseconds, never worth a sub-batch of its own), 0 = host upload over PCIe
   cudaEvent_t ev_ext = nullptr;  // marks the producer stream's position in smb_put_images_device_async
 
+  // keypoint positions, one float2 per descriptor-pool row (only used by smb_result_verify)
+  float2* kp_pool = nullptr;
+  DevBuf<float4> d_pts;               // verification scratch: matched point pairs
+  smb_result* last_result = nullptr;  // the result the device-side plan (d_pairs) currently describes
   // descriptor pool
   uint8_t* pool = nullptr;
   uint32_t pool_rows = 0;
@@ -318,11 +329,16 @@ int grow_pool(smb_handle* h, uint32_t min_extra_rows) {
   if (h->inflight) return fail(h, SMB_EINVAL, "the descriptor pool must grow while a match call is in flight: wait for it first");
   uint8_t* np = nullptr;
   SMB_CUDA(h, cudaMalloc(&np, want * kDim));
+  float2* nk = nullptr;
+  SMB_CUDA(h, cudaMalloc(&nk, want * sizeof(float2)));
   if (h->pool) {
     SMB_CUDA(h, cudaMemcpyAsync(np, h->pool, (size_t)h->pool_rows * kDim, cudaMemcpyDeviceToDevice, h->stream));
+    SMB_CUDA(h, cudaMemcpyAsync(nk, h->kp_pool, (size_t)h->pool_rows * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
     SMB_CUDA(h, cudaStreamSynchronize(h->stream));
     SMB_CUDA(h, cudaFree(h->pool));
+    SMB_CUDA(h, cudaFree(h->kp_pool));
   }
+  h->kp_pool = nk;
   h->dev_plan_pairs = h->dev_plan_items = 0;  // (the plan holds pool rows, which are unchanged, but be safe)
   ++h->layout_epoch;
   const uint32_t old_rows = h->pool_rows;
@@ -407,6 +423,7 @@ int put_image_impl(smb_handle* h, uint64_t key, const void* src, size_t n, size_
     }
     if (n) SMB_CUDA(h, cudaMemcpyAsync(h->pool + (size_t)e.row0 * kDim, src, n * kDim, kind, stream));
     e.up_seq = up_seq;
+    e.has_kp = false;  // new descriptors: the old keypoint positions no longer belong to them
     return SMB_OK;
   }
   if (old != h->images.end()) {
@@ -466,6 +483,8 @@ void destroy_result(smb_result* r) {
   if (r->matches) cudaFreeHost(r->matches);
   if (r->pair_out) cudaFreeHost(r->pair_out);
   if (r->counters) cudaFreeHost(r->counters);
+  if (r->tvg) cudaFreeHost(r->tvg);
+  if (r->inliers) cudaFreeHost(r->inliers);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   delete r;
 }
@@ -594,6 +613,8 @@ void smb_destroy(smb_handle* h) {
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->pool) cudaFree(h->pool);
+  if (h->kp_pool) cudaFree(h->kp_pool);
+  h->d_pts.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_up) cudaStreamDestroy(h->stream_up);
   for (auto& e : h->up_ev)
@@ -1062,7 +1083,9 @@ static int begin_keys(smb_handle* h, std::vector<uint64_t>&& keys, size_t npairs
     return rc;
   }
   res->pending = true;
+  res->verified = false;
   h->inflight = res;
+  h->last_result = res;
   *out = res;
   return SMB_OK;
 }
@@ -1117,7 +1140,9 @@ void smb_result_release(smb_handle* h, smb_result* r) {
   if (!r) return;
   if (h) {
     if (r->pending) smb_result_wait(h, r);  // never recycle buffers the device may still write
+    if (h->last_result == r) h->last_result = nullptr;
     r->npairs = 0;
+    r->verified = false;
     h->result_pool.push_back(r);
   } else {
     destroy_result(r);
@@ -1170,6 +1195,92 @@ int smb_get_timing(const smb_handle* h, smb_timing* t) {
   if (!h || !t) return SMB_EINVAL;
   *t = h->timing;
   return SMB_OK;
+}
+
+void smb_default_tvg_options(smb_tvg_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->min_num_inliers = 15;     // colmap.proto:41
+  o->min_num_trials = 30;      // colmap.proto:32
+  o->max_num_trials = 10000;   // colmap.proto:33
+  o->max_error = 4.0;          // colmap.proto:26
+  o->confidence = 0.999;       // colmap.proto:29
+  o->min_inlier_ratio = 0.25;  // colmap.proto:37
+  o->max_h_inlier_ratio = 0.8;
+  o->seed = 0;
+}
+
+int smb_put_keypoints(smb_handle* h, uint32_t image_id, const float* xy, size_t n, size_t stride_bytes) {
+  if (!h) return SMB_EINVAL;
+  auto it = h->images.find(image_id);
+  if (it == h->images.end()) return fail(h, SMB_EINVAL, "image %u is not cached", image_id);
+  if (it->second.n != n) return fail(h, SMB_EINVAL, "image %u has %u descriptors, got %zu keypoints", image_id, it->second.n, n);
+  if (n && (!xy || stride_bytes < sizeof(float2))) return fail(h, SMB_EINVAL, "bad keypoint array");
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  if (n)
+    SMB_CUDA(h, cudaMemcpy2DAsync(h->kp_pool + it->second.row0, sizeof(float2), xy, stride_bytes, sizeof(float2), n,
+                                  cudaMemcpyHostToDevice, h->stream));
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));  // the caller's buffer is free again on return
+  it->second.has_kp = true;
+  return SMB_OK;
+}
+
+int smb_result_verify(smb_handle* h, smb_result* r, const smb_tvg_options* opts) {
+  if (!h || !r) return SMB_EINVAL;
+  if (r->pending) return fail(h, SMB_EINVAL, "wait for the match call before verifying it");
+  if (h->inflight) return fail(h, SMB_EINVAL, "another match call is in flight");
+  if (h->last_result != r || h->dev_plan_pairs != r->npairs)
+    return fail(h, SMB_EINVAL, "only the most recent completed match call of a handle can be verified");
+  smb_tvg_options def;
+  smb_default_tvg_options(&def);
+  const smb_tvg_options& o = opts ? *opts : def;
+  if (r->npairs == 0) {
+    r->verified = true;
+    return SMB_OK;
+  }
+  for (size_t k = 0; k < 2 * r->npairs; ++k) {
+    auto it = h->images.find(r->keys[k]);
+    if (it == h->images.end() || !it->second.has_kp)
+      return fail(h, SMB_EINVAL, "image %llu has no keypoints (smb_put_keypoints)", (unsigned long long)r->keys[k]);
+  }
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  static_assert(sizeof(smb_tvg) == sizeof(tvg::Out), "smb_tvg mirrors tvg::Out");
+  if (!reserve_pinned(&r->tvg, &r->tvg_cap, r->npairs) || !reserve_pinned(&r->inliers, &r->inliers_cap, std::max<size_t>(r->total, 1)) ||
+      cudaSuccess != h->d_pts.reserve(std::max<size_t>(r->total, 1))) {
+    cudaGetLastError();
+    return fail(h, SMB_ENOMEM, "verification buffers (%zu pairs, %zu matches)", r->npairs, r->total);
+  }
+  tvg::Options to;
+  to.min_num_inliers = o.min_num_inliers;
+  to.min_num_trials = o.min_num_trials;
+  to.max_num_trials = o.max_num_trials;
+  to.max_error = o.max_error;
+  to.confidence = o.confidence;
+  to.min_inlier_ratio = o.min_inlier_ratio;
+  to.max_H_inlier_ratio = o.max_h_inlier_ratio;
+  to.seed = o.seed;
+  tvg::verify_kernel<<<(unsigned)r->npairs, tvg::kThreads, 0, h->stream>>>(
+      h->d_pairs.p, reinterpret_cast<const uint2*>(r->matches), r->pair_out, h->kp_pool, h->d_pts.p, to,
+      reinterpret_cast<tvg::Out*>(r->tvg), reinterpret_cast<uint2*>(r->inliers));
+  SMB_CUDA(h, cudaGetLastError());
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  r->verified = true;
+  return SMB_OK;
+}
+
+int smb_result_tvg(const smb_result* r, size_t i, smb_tvg* out) {
+  if (!r || !out || !r->verified || i >= r->npairs) return SMB_EINVAL;
+  *out = r->tvg[i];
+  return SMB_OK;
+}
+
+const smb_match* smb_result_inliers(const smb_result* r, size_t i, size_t* count) {
+  if (!r || !r->verified || i >= r->npairs) {
+    if (count) *count = 0;
+    return nullptr;
+  }
+  if (count) *count = r->tvg[i].inlier_count;
+  return r->inliers + r->tvg[i].inlier_start;
 }
 
 int smb_alloc_pinned(size_t bytes, void** out) {

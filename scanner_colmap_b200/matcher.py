@@ -45,6 +45,19 @@ class smb_timing(ctypes.Structure):
                 ("candidates", ctypes.c_uint64), ("ops", ctypes.c_uint64)]
 
 
+class smb_tvg_options(ctypes.Structure):
+    _fields_ = [("min_num_inliers", ctypes.c_int32), ("min_num_trials", ctypes.c_int32), ("max_num_trials", ctypes.c_int32),
+                ("pad_", ctypes.c_int32), ("max_error", ctypes.c_double), ("confidence", ctypes.c_double),
+                ("min_inlier_ratio", ctypes.c_double), ("max_h_inlier_ratio", ctypes.c_double), ("seed", ctypes.c_uint64)]
+
+
+class smb_tvg(ctypes.Structure):
+    _fields_ = [("config", ctypes.c_int32), ("num_inliers_f", ctypes.c_int32), ("num_inliers_h", ctypes.c_int32),
+                ("trials_f", ctypes.c_int32), ("trials_h", ctypes.c_int32), ("inlier_start", ctypes.c_uint32),
+                ("inlier_count", ctypes.c_uint32), ("pad_", ctypes.c_uint32), ("F", ctypes.c_double * 9),
+                ("H", ctypes.c_double * 9)]
+
+
 class smb_match(ctypes.Structure):
     _fields_ = [("idx1", ctypes.c_uint32), ("idx2", ctypes.c_uint32)]
 
@@ -100,6 +113,13 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_stream.restype = vp
     L.smb_stream_wait_uploads.argtypes = [vp, vp]
     L.smb_synchronize.argtypes = [vp]
+    L.smb_default_tvg_options.argtypes = [ctypes.POINTER(smb_tvg_options)]
+    L.smb_default_tvg_options.restype = None
+    L.smb_put_keypoints.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_size_t]
+    L.smb_result_verify.argtypes = [vp, vp, ctypes.POINTER(smb_tvg_options)]
+    L.smb_result_tvg.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(smb_tvg)]
+    L.smb_result_inliers.argtypes = [vp, ctypes.c_size_t, szp]
+    L.smb_result_inliers.restype = vp
     L.smb_alloc_pinned.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.smb_free_pinned.argtypes = [vp]
     L.smb_free_pinned.restype = None
@@ -202,6 +222,14 @@ class SiftMatcher:
         ns = (ctypes.c_size_t * n)(*[d.shape[0] for d in ds])
         self._check(self._L.smb_put_images_async(self._h, ids.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p),
                                                  ctypes.cast(ns, ctypes.c_void_p), n, 128))
+
+    def put_keypoints(self, image_id: int, keypoints) -> None:
+        """Keypoint positions of a cached image, for ``MatchResult.verify``: float32 [n, 2] (x, y) or the reference's
+        FeatureKeypoint rows float32 [n, 6] (x, y, a11, a12, a21, a22; io.cc:115-123) -- only x, y are read."""
+        k = np.ascontiguousarray(keypoints, dtype=np.float32)
+        if k.ndim != 2 or k.shape[1] < 2:
+            raise ValueError("keypoints must be [n, >= 2] float32")
+        self._check(self._L.smb_put_keypoints(self._h, int(image_id), k.ctypes.data, k.shape[0], k.strides[0]))
 
     def put_image_device(self, image_id: int, dev_ptr: int, n: int) -> None:
         self._check(self._L.smb_put_image_device(self._h, int(image_id), ctypes.c_void_p(dev_ptr), int(n), 128))
@@ -332,6 +360,34 @@ class MatchResult:
             return np.empty((0, 2), dtype=np.uint32)
         a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(cnt.value, 2))
         return a.copy()
+
+    def verify(self, **opts) -> None:
+        """Two-view geometry verification of every pair on the GPU (TwoViewGeometry::Estimate with the reference's
+        dummy cameras: uncalibrated F / H LORANSAC).  Options: min_num_inliers, min_num_trials, max_num_trials,
+        max_error, confidence, min_inlier_ratio, max_h_inlier_ratio, seed (defaults: colmap.proto:24-44)."""
+        self.wait()
+        o = smb_tvg_options()
+        self._m._L.smb_default_tvg_options(ctypes.byref(o))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown option {k}")
+            setattr(o, k, v)
+        self._m._check(self._m._L.smb_result_verify(self._m._h, self._r, ctypes.byref(o)))
+
+    def tvg(self, i: int) -> dict:
+        t = smb_tvg()
+        if self._m._L.smb_result_tvg(self._r, int(i), ctypes.byref(t)) != SMB_OK:
+            raise SmbError(SMB_EINVAL, "result has not been verified")
+        return {"config": t.config, "num_inliers_F": t.num_inliers_f, "num_inliers_H": t.num_inliers_h,
+                "trials_F": t.trials_f, "trials_H": t.trials_h, "F": np.array(t.F, dtype=np.float64).reshape(3, 3),
+                "H": np.array(t.H, dtype=np.float64).reshape(3, 3)}
+
+    def inliers(self, i: int) -> np.ndarray:
+        cnt = ctypes.c_size_t()
+        ptr = self._m._L.smb_result_inliers(self._r, int(i), ctypes.byref(cnt))
+        if cnt.value == 0:
+            return np.empty((0, 2), dtype=np.uint32)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(cnt.value, 2)).copy()
 
     def release(self) -> None:
         if self._r is not None and self._m._h:

@@ -11,10 +11,10 @@
 // GPU works, then the matches (which the device wrote into pinned host memory) are verified and serialised.
 // All kernel instances of a process share one GPU context per device.
 //
-// Two-view geometry verification (:84-101, :157-178) stays on the CPU and stays COLMAP's: with
-// -DSMB_WITH_COLMAP the unchanged colmap::TwoViewGeometry::Estimate[Multiple] runs on the GPU matches; without
-// COLMAP (this image) the verifier is a pass-through (config = UNDEFINED, inlier_matches = raw matches) so the
-// row format, the pair enumeration and the min_num_inliers filter can still be exercised end to end.
+// Two-view geometry verification (:84-101, :157-178): with -DSMB_WITH_COLMAP the unchanged CPU
+// colmap::TwoViewGeometry::Estimate[Multiple] runs on the GPU's matches; without COLMAP (this image) it runs on the
+// GPU as well (smb_result_verify: the uncalibrated F / H LORANSAC path Estimate takes with the reference's dummy
+// cameras -- a statistical contract, not bit parity); SMB_OP_VERIFY=none emits the raw matches.
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <unordered_map>
 
@@ -136,7 +137,7 @@ struct SharedGpu {
   smb_handle* h = nullptr;
   int refs = 0;
   smb_options opts{};                 // what the handle is currently set to
-  struct Cached { uint64_t n, sig, last_use; };
+  struct Cached { uint64_t n, sig, last_use; bool has_kp; };
   std::unordered_map<uint32_t, Cached> cached;
   uint64_t tick = 0;
   uint8_t* stage = nullptr;           // pinned staging buffer for this execute()'s new images
@@ -223,6 +224,20 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     if (const char* e = std::getenv("SMB_DEVICE")) device = std::atoi(e);
     else if (args_.siftargs.gpu_index != "-1") device = std::atoi(args_.siftargs.gpu_index.c_str());
     verbose_ = std::getenv("SMB_OP_VERBOSE") != nullptr;  // the reference printf's per pair (:130-134,150,171)
+#ifndef SMB_WITH_COLMAP
+    // Without COLMAP the geometric verification runs on the GPU (smb_result_verify: the uncalibrated F / H LORANSAC
+    // path TwoViewGeometry::Estimate takes with the reference's dummy cameras; statistical contract).
+    // SMB_OP_VERIFY=none emits the raw matches instead (config UNDEFINED) -- what the matcher-parity tests compare.
+    const char* vm = std::getenv("SMB_OP_VERIFY");
+    gpu_verify_ = !(vm && std::string(vm) == "none");
+#endif
+    smb_default_tvg_options(&tvg_opts_);
+    tvg_opts_.min_num_inliers = args_.siftargs.min_num_inliers;        // sequential_matching.cc:63-75
+    tvg_opts_.max_error = args_.siftargs.max_error;
+    tvg_opts_.confidence = args_.siftargs.confidence;
+    tvg_opts_.min_num_trials = args_.siftargs.min_num_trials;
+    tvg_opts_.max_num_trials = args_.siftargs.max_num_trials;
+    tvg_opts_.min_inlier_ratio = args_.siftargs.min_inlier_ratio;
     gpu_ = acquire_gpu(device, opts_);
   }
   ~SequentialMatchingB200Kernel() override { release_gpu(gpu_); }
@@ -237,7 +252,7 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     const size_t batch = input_cols[0].size();
     // ---- 1. decode every row's stencil; collect the distinct images of the batch
     struct Row { std::vector<uint32_t> ids; std::vector<uint32_t> partners; std::vector<size_t> partner_stencil; };
-    struct Img { uint32_t id; smb_wire::DescriptorView d; };
+    struct Img { uint32_t id; smb_wire::DescriptorView d; const scanner::Element* kp; };
     std::vector<Row> rows(batch);
     std::vector<Img> used;
     std::unordered_map<uint32_t, size_t> used_pos;
@@ -251,7 +266,7 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
         const uint32_t id = smb_wire::read_image_id(id_st[s].buffer, id_st[s].size);
         r.ids.push_back(id);
         if (used_pos.emplace(id, used.size()).second)
-          used.push_back(Img{id, smb_wire::view_descriptors(desc_st[s].buffer, desc_st[s].size)});
+          used.push_back(Img{id, smb_wire::view_descriptors(desc_st[s].buffer, desc_st[s].size), &input_cols[1][b][s]});
       }
       // sequential_matching.cc:139-146: anchor = stencil[0]; partners in stencil order, skipping the anchor id
       // and ids already seen (absorbs Scanner's REPEAT_EDGE halo at the table tail)
@@ -285,7 +300,7 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
         it->second.last_use = g.tick;
         continue;
       }
-      g.cached[im.id] = SharedGpu::Cached{im.d.rows, sig, g.tick};
+      g.cached[im.id] = SharedGpu::Cached{im.d.rows, sig, g.tick, false};
       fresh.push_back(k);
       fresh_bytes += im.d.rows * SMB_DESC_DIM;
     }
@@ -337,6 +352,20 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     }
     rc = smb_result_wait(h, res);
     SMB_CHECK(rc == SMB_OK, "smb_result_wait: %s", smb_last_error(h));
+    if (gpu_verify_) {
+      for (const Img& im : used) {
+        SharedGpu::Cached& c = g.cached[im.id];
+        if (c.has_kp) continue;
+        const smb_wire::KeypointView kv = smb_wire::view_keypoints(im.kp->buffer, im.kp->size);
+        SMB_CHECK(kv.n == im.d.rows, "image %u: %zu keypoints for %zu descriptors", im.id, kv.n, im.d.rows);
+        rc = smb_put_keypoints(h, im.id, reinterpret_cast<const float*>(kv.data), kv.n, sizeof(smb_wire::FeatureKeypoint));
+        SMB_CHECK(rc == SMB_OK, "smb_put_keypoints: %s", smb_last_error(h));
+        c.has_kp = true;
+      }
+      tvg_opts_.seed = g.tick;
+      rc = smb_result_verify(h, res, &tvg_opts_);
+      SMB_CHECK(rc == SMB_OK, "smb_result_verify: %s", smb_last_error(h));
+    }
     // ---- 5. verify + serialise, one output row per batch item (the reference emits one, for item 0 only)
     size_t p = 0;
     for (size_t b = 0; b < batch; ++b) {
@@ -346,7 +375,8 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
       for (size_t k = 0; k < r.partners.size(); ++k, ++p) {
         size_t m = 0;
         const smb_match* matches = smb_result_matches(res, p, &m);
-        TwoViewGeometry tvg = verify(matches, m, input_cols[1][b][0], input_cols[1][b][r.partner_stencil[k]]);
+        TwoViewGeometry tvg = gpu_verify_ ? from_gpu(res, p)
+                                          : verify(matches, m, input_cols[1][b][0], input_cols[1][b][r.partner_stencil[k]]);
         if (verbose_) std::printf("View geometry for #%u and #%u has %zu inliers\n", r.ids[0], r.partners[k], tvg.inlier_matches.size());
         // sequential_matching.cc:173-178: too few inliers -> default-constructed TwoViewGeometry
         if (tvg.inlier_matches.size() < static_cast<size_t>(args_.siftargs.min_num_inliers)) tvg = TwoViewGeometry();
@@ -373,6 +403,24 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     std::lock_guard<std::mutex> lock(gpu_->mu);
     SMB_CHECK(smb_clear_images(gpu_->h) == SMB_OK, "%s", smb_last_error(gpu_->h));
     gpu_->cached.clear();
+  }
+
+  // The GPU verifier's verdict as a colmap::TwoViewGeometry row: config, F and H (Eigen stores them column-major,
+  // io.cc:283-293), inlier_matches; E / qvec / tvec / tri_angle stay zero as EstimateUncalibrated leaves them.
+  static TwoViewGeometry from_gpu(const smb_result* res, size_t p) {
+    TwoViewGeometry out;
+    smb_tvg t;
+    if (smb_result_tvg(res, p, &t) != SMB_OK) return out;
+    out.config = t.config;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        out.F[3 * c + r] = t.F[3 * r + c];
+        out.H[3 * c + r] = t.H[3 * r + c];
+      }
+    size_t n = 0;
+    const smb_match* in = smb_result_inliers(res, p, &n);
+    out.inlier_matches.assign(reinterpret_cast<const FeatureMatch*>(in), reinterpret_cast<const FeatureMatch*>(in) + n);
+    return out;
   }
 
   // converted from colmap::TwoViewGeometryVerifier::Run via sequential_matching.cc:84-101
@@ -412,8 +460,10 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
 
   smb_proto::SequentialMatchingArgs args_;
   smb_options opts_{};
+  smb_tvg_options tvg_opts_{};
   SharedGpu* gpu_ = nullptr;
   bool verbose_ = false;
+  bool gpu_verify_ = false;
 };
 
 }  // namespace

@@ -15,6 +15,14 @@ def oracle(built):
     return o
 
 
+@pytest.fixture(autouse=True)
+def raw_matches(monkeypatch, request):
+    """The matcher-parity tests compare the op's rows with the oracle's MATCHES: geometric verification off
+    (SMB_OP_VERIFY=none); test_op_verifies_on_the_gpu switches it back on."""
+    if "verifies" not in request.node.name:
+        monkeypatch.setenv("SMB_OP_VERIFY", "none")
+
+
 def _expected_rows(oracle, ids, descs, overlap, min_num_inliers=15, **opts):
     rows = []
     for r in range(len(ids)):
@@ -126,3 +134,31 @@ def test_kernel_instances_share_one_gpu_context(oracle):
                     assert got_ids[r] == partners
                     for g, w in zip(got_tvg[r], tv):
                         assert np.array_equal(g.inlier_matches, w)
+
+
+def test_op_verifies_on_the_gpu(built):
+    """Default op behaviour without COLMAP: every pair's matches go through the GPU two-view verification; rows carry
+    config / F / H / inlier_matches, and pairs below min_num_inliers become default geometries (:173-178)."""
+    from oracle import two_view_oracle as tv
+    n = 2048
+    p1, p2, m, truth = tv.synthetic_pair(n, n, 700, 200, 31)
+    q1, q2, m2, truth2 = tv.synthetic_pair(n, n, 0, 60, 32)          # geometrically meaningless matches
+    d = [synth.make_image(8100 + i, n, shared_frac=0.0) for i in range(3)]
+    d[1][m[:, 1]] = d[0][m[:, 0]]                                     # image 0 <-> 1: a real scene
+    free = np.setdiff1d(np.arange(n), m[:, 1])[:60]
+    d[2][m2[:60, 1]] = d[1][free]                                     # image 1 <-> 2: 60 arbitrary matches
+    kp = [np.zeros((n, 6), np.float32) for _ in range(3)]
+    kp[0][:, :2], kp[1][:, :2] = p1, p2
+    kp[2][:, :2] = q2
+    got_ids, got_tvg = scanner_sim.run_feature_matching([40, 41, 42], kp, d, overlap=2, packet_size=3)
+    assert got_ids == [[41], [42], []]
+    g = got_tvg[0][0]
+    assert g.config == tv.UNCALIBRATED and g.F.any() and not g.E.any()
+    true_set = set(map(tuple, m[truth].tolist()))
+    inl = set(map(tuple, g.inlier_matches.tolist()))
+    assert len(inl & true_set) >= 0.95 * len(true_set) * 0.98 and len(inl - true_set) <= 0.05 * len(inl)
+    x1, x2 = p1[g.inlier_matches[:, 0]].astype(np.float64), p2[g.inlier_matches[:, 1]].astype(np.float64)
+    F = g.F.reshape(3, 3).T                                        # serialised in Eigen's column-major order (io.cc:283-293)
+    assert np.median(tv.sampson_sq(F, x1, x2)) < 1.5               # ... and it explains its inliers
+    g2 = got_tvg[1][0]
+    assert len(g2.inlier_matches) == 0 or len(g2.inlier_matches) >= 15
