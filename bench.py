@@ -469,7 +469,7 @@ def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=
     exchange()
     m.match_pairs_count(pairs)                                  # warm-up (allocations, pool growth)
     cx.barrier()
-    ms, score_ms, ops, launches, last = 0.0, 0.0, 0, 0, None
+    ms, score_ms, ops, launches, last, other = 0.0, 0.0, 0, 0, None, {"runner_up_ms": 0.0, "decide_ms": 0.0, "plan_uploads": 0}
     for _ in range(steps):
         cx.flush_l2()
         cx.barrier()
@@ -486,6 +486,9 @@ def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=
         score_ms += t["score_ms"]
         ops += t["ops"]
         launches += t["score_launches"]
+        other["runner_up_ms"] += t["runner_up_ms"]
+        other["decide_ms"] += t["decide_ms"]
+        other["plan_uploads"] += t["plan_uploaded"]
     cx.barrier()
     # parity sample; halo rows are regenerated on this GPU, which also checks the bytes NVLink delivered
     def host_image(i):
@@ -518,6 +521,8 @@ def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=
         "rank_score_ms": [round(float(x), 3) for x in allr[:, 1]],
         "score_launches_per_step_rank0": launches // max(steps, 1), "matches_rank0": int(total_matches),
         "halo_bytes_in_rank0": int(sum(int(sizes[r]) * 128 for r in halo_ids)),
+        "rank0_ms_per_step": {"runner_up_kernel": other["runner_up_ms"] / steps, "decide_kernel": other["decide_ms"] / steps,
+                              "plan_uploads": other["plan_uploads"]},
     }
     if exhaustive:
         rec.update({"distribution": "2-D tiling of the pair triangle over image blocks (sharding.plan_exhaustive); each rank "
