@@ -489,6 +489,7 @@ def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=
         other["runner_up_ms"] += t["runner_up_ms"]
         other["decide_ms"] += t["decide_ms"]
         other["plan_uploads"] += t["plan_uploaded"]
+        other["cta_busy_max_over_mean"] = t["cta_busy_max_over_mean"]
     cx.barrier()
     # parity sample; halo rows are regenerated on this GPU, which also checks the bytes NVLink delivered
     def host_image(i):
@@ -523,6 +524,7 @@ def run_extra(cx: Ctx, name, sizes, overlap, exhaustive=False, steps=2, n_check=
         "halo_bytes_in_rank0": int(sum(int(sizes[r]) * 128 for r in halo_ids)),
         "rank0_ms_per_step": {"runner_up_kernel": other["runner_up_ms"] / steps, "decide_kernel": other["decide_ms"] / steps,
                               "plan_uploads": other["plan_uploads"]},
+        "score_cta_busy_max_over_mean_rank0": other.get("cta_busy_max_over_mean"),
     }
     if exhaustive:
         rec.update({"distribution": "2-D tiling of the pair triangle over image blocks (sharding.plan_exhaustive); each rank "

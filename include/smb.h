@@ -85,6 +85,9 @@ typedef struct smb_timing {
   uint32_t plan_uploaded;  /* 0: the device-side plan of the previous call was reused (same pairs, same pool rows) */
   uint64_t candidates;  /* score-matrix entries that survived the integer pre-filter */
   uint64_t ops;         /* 2 * sum(n1 * n2) * 128 over the call's pairs */
+  float cta_busy_max_over_mean; /* load balance of the persistent score CTAs: sum over the call's score launches of the
+                                   busiest CTA's time / sum of the mean CTA time (1.0 = perfectly balanced) */
+  float pad_;
 } smb_timing;
 
 void smb_default_options(smb_options* opts);

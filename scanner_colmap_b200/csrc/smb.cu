@@ -124,6 +124,7 @@ struct smb_result {
   std::vector<cudaEvent_t> ev;  // profiling: 4 per sub-batch + 2
   size_t n_subs = 0;
   std::vector<uint8_t> sub_has_items;
+  std::vector<uint32_t> sub_grid;  // CTAs of each sub-batch's score launch (0 = none)
   uint64_t ops = 0;
   uint32_t launches = 0, score_launches = 0, plan_uploaded = 0;
 };
@@ -172,6 +173,8 @@ struct smb_handle {
   unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed,
                                              // [4] result buffer overflowed
   DevBuf<uint4> d_log;                       // survivor log (kernels.cuh SurvivorLog)
+  DevBuf<unsigned long long> d_cta_busy;     // profiling: per score launch, per CTA busy nanoseconds
+  PinnedBuf<unsigned long long> h_cta_busy;
   size_t log_cap = (size_t)16 << 20;         // entries; SMB_LOG_CAP overrides (tests force the overflow path)
   PinnedBuf<PairMeta> h_pairs;   // the plan the device copy (d_pairs / d_items) was fetched from
   PinnedBuf<WorkItem> h_items;
@@ -608,6 +611,8 @@ void smb_destroy(smb_handle* h) {
   h->d_items.release();
   h->d_acc.release();
   h->d_log.release();
+  h->d_cta_busy.release();
+  h->h_cta_busy.release();
   h->h_pairs.release();
   h->h_items.release();
   if (h->d_counters) cudaFree(h->d_counters);
@@ -921,8 +926,14 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       res->ev.push_back(e);
     }
   }
+  if (prof && (cudaSuccess != h->d_cta_busy.reserve(subs.size() * (size_t)h->num_sms) ||
+               cudaSuccess != h->h_cta_busy.reserve(subs.size() * (size_t)h->num_sms))) {
+    cudaGetLastError();
+    return fail(h, SMB_ENOMEM, "profiling scratch allocation failed");
+  }
   res->n_subs = subs.size();
   res->sub_has_items.assign(subs.size(), 0);
+  res->sub_grid.assign(subs.size(), 0);
   res->ops = ops;
   res->launches = res->score_launches = res->plan_uploaded = 0;
 
@@ -991,7 +1002,9 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
         const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms);  // persistent CTAs
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p + sb.item0, (uint32_t)sb.items,
                                                                           h->d_pairs.p + sb.first, acc, slog,
-                                                                          h->filter.min_score, cand, h->dbg_flags);
+                                                                          h->filter.min_score, cand, h->dbg_flags,
+                                                                          prof ? h->d_cta_busy.p + k * (size_t)h->num_sms : nullptr);
+        res->sub_grid[k] = grid;
       }
       SMB_CUDA_R(cudaGetLastError());
       res->score_launches++;
@@ -1015,6 +1028,9 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   }
   SMB_CUDA_R(cudaMemcpyAsync(res->counters, h->d_counters, smb_handle::kNumCounters * sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, st));
+  if (prof)
+    SMB_CUDA_R(cudaMemcpyAsync(h->h_cta_busy.p, h->d_cta_busy.p, subs.size() * (size_t)h->num_sms * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, st));
   if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[1], st));
 #undef SMB_CUDA_R
   return SMB_OK;
@@ -1057,6 +1073,17 @@ static int finish_match(smb_handle* h, smb_result* res) {
     }
     cudaGetLastError();
     h->timing.candidates = res->counters[1];
+    double sum_max = 0.0, sum_mean = 0.0;
+    for (size_t k = 0; k < res->n_subs && k < res->sub_grid.size(); ++k) {
+      const uint32_t g = res->sub_grid[k];
+      if (!g) continue;
+      const unsigned long long* b = h->h_cta_busy.p + k * (size_t)h->num_sms;
+      unsigned long long mx = 0, tot = 0;
+      for (uint32_t c = 0; c < g; ++c) { mx = std::max(mx, b[c]); tot += b[c]; }
+      sum_max += (double)mx;
+      sum_mean += (double)tot / g;
+    }
+    h->timing.cta_busy_max_over_mean = sum_mean > 0.0 ? (float)(sum_max / sum_mean) : 0.f;
   }
   return SMB_OK;
 }

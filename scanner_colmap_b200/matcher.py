@@ -42,7 +42,8 @@ class smb_timing(ctypes.Structure):
     _fields_ = [("total_ms", ctypes.c_float), ("score_ms", ctypes.c_float), ("runner_up_ms", ctypes.c_float),
                 ("decide_ms", ctypes.c_float), ("score_launches", ctypes.c_uint32), ("total_launches", ctypes.c_uint32),
                 ("sub_batches", ctypes.c_uint32), ("plan_uploaded", ctypes.c_uint32),
-                ("candidates", ctypes.c_uint64), ("ops", ctypes.c_uint64)]
+                ("candidates", ctypes.c_uint64), ("ops", ctypes.c_uint64), ("cta_busy_max_over_mean", ctypes.c_float),
+                ("pad_", ctypes.c_float)]
 
 
 class smb_tvg_options(ctypes.Structure):

@@ -146,6 +146,7 @@ def test_config1_20x4096_overlap10(oracle):
         t = m.timing()
     assert total > 1000
     assert t["score_launches"] >= 1 and t["ops"] == 135 * 2 * 4096 * 4096 * 128
+    assert 1.0 <= t["cta_busy_max_over_mean"] < 1.6        # per-CTA busy time of the persistent score kernel (load balance)
 
 
 def test_pool_growth_and_many_images(oracle):

@@ -12,4 +12,5 @@ for _ in range(3):
     t0 = time.perf_counter(); tot = m.match_pairs_count(pairs); wall = (time.perf_counter() - t0) * 1e3
     t = m.timing()
     print(f"{n} ragged images, {len(pairs)} pairs, sizes {min(sizes)}..{max(sizes)}: wall={wall:.2f}ms score={t['score_ms']:.2f}ms "
-          f"TOPS={t['ops']/t['score_ms']/1e9:.0f} matches={tot}", flush=True)
+          f"TOPS={t['ops']/t['score_ms']/1e9:.0f} matches={tot} launches={t['score_launches']} "
+          f"cta_busy_max_over_mean={t['cta_busy_max_over_mean']:.4f}", flush=True)
