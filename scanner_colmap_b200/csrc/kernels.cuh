@@ -341,31 +341,6 @@ runner_up_kernel(const uint4* __restrict__ entries, const unsigned long long* __
   }
 }
 
-// SMB_POST_BALLOT=1: survivor runs are posted run by run with one ballot each (no per-lane mask shuffle).
-#ifndef SMB_POST_BALLOT
-#define SMB_POST_BALLOT 0
-#endif
-// Copy the 32-column run `v` of every lane whose bit is set in `lanes` into epilogue warp e's mailbox (one slot per
-// lane), with back-pressure on the consumer's tail.  The new head is NOT published here.
-__device__ __forceinline__ void stage_runs(ScoreShared* sh, uint32_t e, uint32_t lane, uint32_t lanes, const uint32_t (&v)[32],
-                                           uint32_t row_slot, uint32_t col_slot0, uint32_t& mail_head, uint32_t& mail_tail_seen) {
-  while (lanes) {
-    const int src = __ffs(lanes) - 1;
-    lanes &= lanes - 1;
-    if (mail_head + 1 - mail_tail_seen > (uint32_t)kMailSlots) {  // ring (seems) full: back-pressure
-      __syncwarp();  // publish what has been written so far, or the consumer could never make room
-      if (lane == 0) st_release_shared(&sh->mail_head[e], mail_head);
-      uint32_t spins = 0;
-      do {
-        mail_tail_seen = ld_volatile_shared(&sh->mail_tail[e]);
-        if (++spins > (1u << 28)) __trap();
-      } while (mail_head + 1 - mail_tail_seen > (uint32_t)kMailSlots);
-    }
-    if (lane == (uint32_t)src) store_run(sh, e, mail_head, v, row_slot, col_slot0);
-    ++mail_head;
-  }
-}
-
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
                      const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, SurvivorLog slog, int min_score,
@@ -584,16 +559,6 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
             const uint32_t hm = (mc0 >= min_score ? 1u : 0u) | (mc1 >= min_score ? 2u : 0u) | (mc2 >= min_score ? 4u : 0u) |
                                 (mc3 >= min_score ? 8u : 0u);
             const uint32_t rslot = row_slot + mh * kMTile, cslot = col_slot0 + t * kTileCols;
-#if SMB_POST_BALLOT
-            (void)hm;
-            stage_runs(sh, e, lane, __ballot_sync(0xffffffffu, mc0 >= min_score), v0, rslot, cslot, mail_head, mail_tail_seen);
-            stage_runs(sh, e, lane, __ballot_sync(0xffffffffu, mc1 >= min_score), v1, rslot, cslot + kRunCols, mail_head, mail_tail_seen);
-            if constexpr (kRunsPerWarp == 4) {
-              stage_runs(sh, e, lane, __ballot_sync(0xffffffffu, mc2 >= min_score), v2, rslot, cslot + 2 * kRunCols, mail_head, mail_tail_seen);
-              stage_runs(sh, e, lane, __ballot_sync(0xffffffffu, mc3 >= min_score), v3, rslot, cslot + 3 * kRunCols, mail_head, mail_tail_seen);
-            }
-            if (false)
-#endif
             do {
               const int src = __ffs(lanes) - 1;
               lanes &= lanes - 1;
