@@ -802,7 +802,17 @@ decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, cons
   }
   __syncthreads();
   uint32_t running = s_base;
-  if (running == 0xFFFFFFFFu) return;  // whole CTA: this attempt is being discarded
+  // Whatever happens below, this CTA leaves its pair's accumulator slots zeroed (after its last read of them): the
+  // next sub-batch / call that reuses the region then needs no 16-byte-per-slot memset of its own -- the stores hide
+  // under this kernel's PCIe-bound match writes.
+  auto clear_slots = [&]() {
+    __syncthreads();
+    for (uint32_t x = tid; x < pm.n1 + pm.n2; x += kDecideThreads) rows[x] = TopTwo{0ull, 0ull};
+  };
+  if (running == 0xFFFFFFFFu) {  // whole CTA: this attempt is being discarded
+    clear_slots();
+    return;
+  }
 
   // pass 2: ordered write (ascending idx1), block-wide exclusive scan per chunk of rows.  The matches of a chunk are
   // compacted into shared memory first and flushed in dense runs: every lane of a warp then stores 8 consecutive
@@ -834,6 +844,7 @@ decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, cons
       buffered = 0;
     }
   }
+  clear_slots();
 }
 
 }  // namespace smb

@@ -169,6 +169,7 @@ struct smb_handle {
   DevBuf<PairMeta> d_pairs;
   DevBuf<WorkItem> d_items;
   DevBuf<TopTwo> d_acc;
+  size_t acc_zero_slots = 0;  // leading slots of d_acc known to be zero: decide_kernel clears what a sub-batch dirtied
   static constexpr int kNumCounters = 6;
   unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed,
                                              // [4] result buffer overflowed
@@ -768,6 +769,7 @@ int smb_image_device_ptr(const smb_handle* h, uint32_t image_id, const void** de
 // device for their own ticket only.  A pending device-to-device adoption (smb_put_images_device_async: the NVLink
 // halo, microseconds) never splits a call -- every extra score launch pays its own tail (~0.2 ms measured), more
 // than such a wait costs.
+static cudaError_t reserve_acc(smb_handle* h, size_t n);
 static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t matches_want) {
   const uint64_t* keys = res->keys.data();
   const size_t npairs = res->npairs;
@@ -913,7 +915,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   if (!reserve_pinned(&res->matches, &res->matches_cap, matches_want) || !reserve_pinned(&res->pair_out, &res->pair_cap, npairs))
     return fail(h, SMB_ENOMEM, "pinned result allocation failed (%zu matches, %zu pairs)", matches_want, npairs);
   if (cudaSuccess != h->d_pairs.reserve(npairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(n_items_total, 1)) ||
-      cudaSuccess != h->d_acc.reserve(std::max<size_t>(acc_region, 1)) || cudaSuccess != h->h_pairs.reserve(npairs) ||
+      cudaSuccess != reserve_acc(h, std::max<size_t>(acc_region, 1)) || cudaSuccess != h->h_pairs.reserve(npairs) ||
       cudaSuccess != h->h_items.reserve(std::max<size_t>(n_items_total, 1)) ||
       (use_log && cudaSuccess != h->d_log.reserve(h->log_cap))) {
     cudaGetLastError();
@@ -943,6 +945,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
     cudaError_t e__ = (expr);                                                                    \
     if (e__ != cudaSuccess) {                                                                    \
       cudaStreamSynchronize(st);                                                                 \
+      h->acc_zero_slots = 0; /* kernels may have dirtied accumulators no decide_kernel cleared */  \
       return fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     }                                                                                            \
   } while (0)
@@ -985,7 +988,10 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[sb.wait_ticket % smb_handle::kUpRing], 0));
       waited = sb.wait_ticket;
     }
-    if (sb.acc) SMB_CUDA_R(cudaMemsetAsync(acc, 0, sb.acc * sizeof(TopTwo), st));
+    if (sb.acc > h->acc_zero_slots) {  // only the part no earlier decide_kernel has left clean
+      SMB_CUDA_R(cudaMemsetAsync(acc + h->acc_zero_slots, 0, (sb.acc - h->acc_zero_slots) * sizeof(TopTwo), st));
+      h->acc_zero_slots = sb.acc;
+    }
     if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[2 + 4 * k], st));
     if (sb.items) {
       res->sub_has_items[k] = 1;
@@ -1036,6 +1042,13 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   return SMB_OK;
 }
 
+static cudaError_t reserve_acc(smb_handle* h, size_t n) {
+  TopTwo* before = h->d_acc.p;
+  cudaError_t e = h->d_acc.reserve(n);
+  if (h->d_acc.p != before) h->acc_zero_slots = 0;  // a new allocation holds garbage
+  return e;
+}
+
 static void flush_pending_free(smb_handle* h) {
   for (auto& f : h->pending_free) free_rows(h, f.first, f.second);
   h->pending_free.clear();
@@ -1047,7 +1060,10 @@ static void flush_pending_free(smb_handle* h) {
 static int finish_match(smb_handle* h, smb_result* res) {
   for (int attempt = 0;; ++attempt) {
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) return fail(h, SMB_ECUDA, "match call failed on the device: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      h->acc_zero_slots = 0;
+      return fail(h, SMB_ECUDA, "match call failed on the device: %s", cudaGetErrorString(e));
+    }
     const unsigned long long* c = res->counters;
     const bool log_over = res->used_log && c[3] != 0, out_over = c[4] != 0;
     if (!log_over && !out_over) break;
