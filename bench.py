@@ -295,6 +295,10 @@ class Ctx:
             if halo_ids:
                 got = cache["got"]
                 m.put_images_device_async(halo_ids, [got[r].data_ptr() for r in halo_ids], halo_ns, cur.cuda_stream)
+            elif cache["ops"]:
+                # a rank that only sends: its persistent score kernel must not start before the send kernel has run,
+                # or the receiving rank would wait a whole step for its halo
+                m.wait_stream(cur.cuda_stream)
         return f
 
     def check_parity(self, tag, res, pairs, sample, host_image, halo_rows=()):

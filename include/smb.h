@@ -115,8 +115,9 @@ int smb_put_images(smb_handle* h, const uint32_t* image_ids, const uint8_t* cons
                    size_t count, size_t d);
 /* Asynchronous form: the copies are queued on a dedicated upload stream and the call returns at once; the
  * caller keeps the (pinned) buffers unchanged until smb_synchronize() or until a match call that names the
- * images has returned.  smb_match_pairs waits (on the device) only for the uploads its own pairs depend on, so
- * uploading the next images overlaps matching the previous ones. */
+ * images has returned.  A match call takes its pairs in the order their images land and its score kernel waits,
+ * item by item on the device, for the upload an item depends on: ONE launch covers a call whose images are still
+ * crossing PCIe, and uploading the next images overlaps matching the previous ones. */
 int smb_put_images_async(smb_handle* h, const uint32_t* image_ids, const uint8_t* const* descs, const size_t* ns,
                          size_t count, size_t d);
 /* Same, from device memory of this or a peer device (halo exchange over NVLink). */
@@ -211,6 +212,11 @@ void* smb_stream(const smb_handle* h);
  * smb_put_images*_async calls: lets a peer copy / NCCL send read freshly uploaded pool rows (the halo this GPU
  * provides to its neighbour) without any host synchronisation. */
 int smb_stream_wait_uploads(smb_handle* h, void* stream);
+/* The converse: every kernel of the match calls that follow waits, on the device, for the work queued so far on
+ * `stream`.  A rank that only SENDS halo rows must call this after queueing the send: the score kernel is persistent
+ * and fills every SM, so a send kernel that has not started yet would otherwise run only after it -- and stall the
+ * receiving rank for a whole step.  (Receivers get the same ordering from smb_put_images_device_async.) */
+int smb_wait_stream(smb_handle* h, void* stream);
 int smb_synchronize(smb_handle* h);
 
 #ifdef __cplusplus

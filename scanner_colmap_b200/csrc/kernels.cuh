@@ -45,7 +45,7 @@ struct alignas(16) WorkItem {  // one strip (<= 256 rows) of image 1 against all
   uint32_t row_slot0;  // accumulator slot of the strip's first row   (= acc_off + a_row - a_row0)
   uint32_t col_slot0;  // accumulator slot of image 2's first column  (= acc_off + n1)
   uint32_t pair;       // index into PairMeta (batch-local)
-  uint32_t pad_;
+  uint32_t wait_ticket;  // 0, or the host-upload ticket whose copies must have landed before this item's rows are read
 };
 static_assert(sizeof(WorkItem) == 32, "WorkItem is two 16-byte words");
 
@@ -344,7 +344,13 @@ runner_up_kernel(const uint4* __restrict__ entries, const unsigned long long* __
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* __restrict__ items, uint32_t n_items,
                      const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, SurvivorLog slog, int min_score,
-                     unsigned long long* cand_counter, uint32_t dbg, unsigned long long* __restrict__ cta_busy_ns) {
+                     unsigned long long* cand_counter, uint32_t dbg, unsigned long long* __restrict__ cta_busy_ns,
+                     const unsigned long long* landed) {
+  // landed: device word holding the newest upload ticket whose copies have completed (written by the copy engine,
+  // in stream order behind the ticket's descriptor copies).  An item that names rows of a still pending HOST upload
+  // carries that ticket; the TMA producer waits for it right before loading the item -- so one launch covers pairs
+  // whose images are still crossing PCIe, instead of one score / runner-up / decide round per upload.  (Only copy-
+  // engine work is ever waited for: it needs no SM, so the persistent CTAs cannot starve it.)
   // cta_busy_ns (profiling, may be null): [blockIdx.x] = nanoseconds this persistent CTA was busy (load balance).
   // dbg (bring-up timing experiments only, results become meaningless):
   // 2 = B tiles are not loaded, 4 = survivor runs are not posted, 8 = survivors are not inserted
@@ -394,8 +400,23 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
     // ------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      uint32_t landed_seen = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
+        if (w.wait_ticket && (int32_t)(w.wait_ticket - landed_seen) > 0) {  // rows of an upload still in flight
+          unsigned long long t0 = 0, now;
+          for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(landed) : "memory");
+            landed_seen = (uint32_t)v;
+            if ((int32_t)(w.wait_ticket - landed_seen) <= 0) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            if (now - t0 > 20000000000ull) __trap();  // 20 s: the upload never came -- fail the launch, never hang the box
+            __nanosleep(500);
+          }
+          ptx::fence_proxy_async_global();  // the TMA (async proxy) reads what the acquire made visible
+        }
         ptx::mbar_wait(ptx::smem_u32(&sh->a_empty[as]), aph ^ 1);
         const uint32_t afull = ptx::smem_u32(&sh->a_full[as]);
         ptx::mbar_arrive_expect_tx(afull, w.m_tiles * (kABytes / 2));

@@ -145,9 +145,12 @@ struct smb_handle {
   std::vector<uint32_t> plan_order;   // scratch of match_keys_impl
   std::vector<uint64_t> plan_ticket;
   uint64_t up_synced = 0;             // tickets <= this are known to have landed
+  unsigned long long* d_landed = nullptr;       // device word: newest ticket whose copies have completed (see score kernel)
+  unsigned long long* h_ticket_vals = nullptr;  // pinned [kUpRing]: the values copied into it
   uint8_t up_fast[kUpRing] = {};      // ticket kind: 1 = device-to-device adoption (NVLink halo: lands within
                                       // microseconds, never worth a sub-batch of its own), 0 = host upload over PCIe
   cudaEvent_t ev_ext = nullptr;  // marks the producer stream's position in smb_put_images_device_async
+  cudaEvent_t ev_ext2 = nullptr; // smb_wait_stream
 
   // keypoint positions, one float2 per descriptor-pool row (only used by smb_result_verify)
   float2* kp_pool = nullptr;
@@ -460,7 +463,12 @@ struct OpenTicket {
   cudaError_t finish() {
     recorded = true;
     h->up_open = 0;
-    return cudaEventRecord(h->up_ev[ticket % smb_handle::kUpRing], h->stream_up);
+    // in stream order behind the ticket's copies: the device-visible "landed" word, then the event
+    unsigned long long* v = h->h_ticket_vals + ticket % smb_handle::kUpRing;
+    *v = ticket;
+    cudaError_t e = cudaMemcpyAsync(h->d_landed, v, sizeof *v, cudaMemcpyHostToDevice, h->stream_up);
+    cudaError_t e2 = cudaEventRecord(h->up_ev[ticket % smb_handle::kUpRing], h->stream_up);
+    return e != cudaSuccess ? e : e2;
   }
   ~OpenTicket() {
     if (!recorded) finish();
@@ -571,6 +579,7 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
   for (auto& e : h->up_ev) SMB_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+  SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext2, cudaEventDisableTiming));
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -590,6 +599,9 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   SMB_CUDA_C(cudaMalloc(&h->lut_dev, kLutSize * sizeof(float)));
   SMB_CUDA_C(cudaMemcpyAsync(h->lut_dev, h->lut_host.data(), kLutSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   SMB_CUDA_C(cudaMalloc(&h->d_counters, smb_handle::kNumCounters * sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMalloc(&h->d_landed, sizeof(unsigned long long)));
+  SMB_CUDA_C(cudaMemsetAsync(h->d_landed, 0, sizeof(unsigned long long), h->stream));
+  SMB_CUDA_C(cudaMallocHost(&h->h_ticket_vals, smb_handle::kUpRing * sizeof(unsigned long long)));
   SMB_CUDA_C(cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
   SMB_CUDA_C(cudaStreamSynchronize(h->stream));
 #undef SMB_CUDA_C
@@ -617,6 +629,8 @@ void smb_destroy(smb_handle* h) {
   h->h_pairs.release();
   h->h_items.release();
   if (h->d_counters) cudaFree(h->d_counters);
+  if (h->d_landed) cudaFree(h->d_landed);
+  if (h->h_ticket_vals) cudaFreeHost(h->h_ticket_vals);
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->pool) cudaFree(h->pool);
   if (h->kp_pool) cudaFree(h->kp_pool);
@@ -626,6 +640,7 @@ void smb_destroy(smb_handle* h) {
   for (auto& e : h->up_ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
+  if (h->ev_ext2) cudaEventDestroy(h->ev_ext2);
   delete h;
 }
 
@@ -786,6 +801,11 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   size_t out_cap = 0, max_acc = 0;
   uint64_t ops = 0;
   auto is_host_ticket = [&](uint64_t t) { return t > h->up_synced && !h->up_fast[t % smb_handle::kUpRing]; };
+#ifdef SMB_TEST_ENGINES
+  const bool kernel_waits = h->opts.engine == SMB_ENGINE_TCGEN05;
+#else
+  const bool kernel_waits = true;
+#endif
   bool pending_host = false;
   for (uint64_t t = h->up_synced + 1; t <= h->up_issued; ++t) pending_host = pending_host || !h->up_fast[t % smb_handle::kUpRing];
   const bool reuse = h->plan_epoch == h->layout_epoch && !pending_host && h->plan_acc_budget == sub_budget &&
@@ -844,14 +864,25 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       if (is_host_ticket(a.up_seq)) host_ticket = a.up_seq;
       if (is_host_ticket(b.up_seq)) host_ticket = std::max(host_ticket, b.up_seq);
       const size_t need = (size_t)a.n + b.n;
-      const bool newer_upload = host_ticket > cur.split_ticket;
+      // Pending HOST uploads are waited for inside the score kernel, item by item (WorkItem::wait_ticket); with the
+      // test engine, which has no such wait, they split the call like the accumulator budget does.
+      const bool newer_upload = !kernel_waits && host_ticket > cur.split_ticket;
       if (p > cur.first && (cur.acc + need > sub_budget || newer_upload)) {
         cur.last = p;
         subs.push_back(cur);
         cur = Sub{p, 0, wi.size(), 0, 0, cur.split_ticket, cur.wait_ticket};
       }
       cur.split_ticket = std::max(cur.split_ticket, host_ticket);
-      if (ticket > h->up_synced) cur.wait_ticket = std::max(cur.wait_ticket, ticket);
+      // stream-level wait (before the sub-batch's first kernel): device-to-device adoptions -- their producer may be a
+      // kernel (NCCL recv) that the persistent score CTAs would starve -- and, without in-kernel waits, everything
+      {
+        uint64_t dev_ticket = 0;
+        for (uint64_t t : {a.up_seq, b.up_seq})
+          if (t > h->up_synced && (!kernel_waits || h->up_fast[t % smb_handle::kUpRing])) dev_ticket = std::max(dev_ticket, t);
+        cur.wait_ticket = std::max(cur.wait_ticket, dev_ticket);
+      }
+      const uint32_t item_ticket = kernel_waits ? (uint32_t)host_ticket : 0u;
+      (void)ticket;
       PairMeta& m = pm[p];
       m.a_row0 = a.row0;
       m.n1 = a.n;
@@ -866,7 +897,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
         const uint32_t n_btiles = (b.n + kTileCols - 1) / kTileCols;
         for (uint32_t r = 0; r < a.n; r += kStripRows)
           wi.push_back(WorkItem{a.row0 + r, b.row0, n_btiles, a.n - r > (uint32_t)kMTile ? 2u : 1u, m.acc_off + r,
-                                m.acc_off + a.n, (uint32_t)(p - cur.first), 0u});
+                                m.acc_off + a.n, (uint32_t)(p - cur.first), item_ticket});
       }
       out_cap += cc ? std::min(a.n, b.n) : a.n;
       ops += 2ull * a.n * b.n * kDim;
@@ -877,15 +908,29 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       Sub& sb = subs[k];
       sb.items = (k + 1 < subs.size() ? subs[k + 1].item0 : wi.size()) - sb.item0;
       max_acc = std::max(max_acc, sb.acc);
-      // ragged sets: largest column counts first inside each sub-batch (stable: a pair's strips stay adjacent)
+      // ragged sets: largest column counts first inside each sub-batch (stable: a pair's strips stay adjacent); items
+      // that wait for an upload stay in landing order, behind everything that can start at once
       WorkItem* it0 = wi.data() + sb.item0;
       bool uniform = true;
       for (size_t x = 1; x < sb.items && uniform; ++x) uniform = it0[x].n_btiles == it0[0].n_btiles;
       if (!uniform)
-        std::stable_sort(it0, it0 + sb.items, [](const WorkItem& x, const WorkItem& y) { return x.n_btiles > y.n_btiles; });
+        std::stable_sort(it0, it0 + sb.items, [](const WorkItem& x, const WorkItem& y) {
+          return x.wait_ticket != y.wait_ticket ? x.wait_ticket < y.wait_ticket : x.n_btiles > y.n_btiles;
+        });
     }
   }
   if (out_cap > 0xFFFFFF00ull) return fail(h, SMB_EINVAL, "match capacity exceeds 2^32 in one call");
+  {
+    // The upload stream is in order: a host upload an item waits for inside the kernel may be queued BEHIND a
+    // device-to-device adoption whose producer is a kernel (the NCCL recv of the halo).  That adoption must have
+    // completed before the persistent score CTAs occupy every SM, or they could starve the very kernel they wait for.
+    uint32_t max_item_ticket = 0;
+    for (const WorkItem& w : wi) max_item_ticket = std::max(max_item_ticket, w.wait_ticket);
+    uint64_t guard = 0;
+    for (uint64_t t = h->up_synced + 1; t <= h->up_issued && t < max_item_ticket; ++t)
+      if (h->up_fast[t % smb_handle::kUpRing]) guard = t;
+    if (guard) subs[0].wait_ticket = std::max(subs[0].wait_ticket, guard);
+  }
   if (!pending_host && order.empty()) {  // reusable as long as the layout and the pair list stay the same
     h->plan_keys.assign(keys, keys + 2 * npairs);
     h->plan_subs = subs;
@@ -1009,7 +1054,8 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p + sb.item0, (uint32_t)sb.items,
                                                                           h->d_pairs.p + sb.first, acc, slog,
                                                                           h->filter.min_score, cand, h->dbg_flags,
-                                                                          prof ? h->d_cta_busy.p + k * (size_t)h->num_sms : nullptr);
+                                                                          prof ? h->d_cta_busy.p + k * (size_t)h->num_sms : nullptr,
+                                                                          h->d_landed);
         res->sub_grid[k] = grid;
       }
       SMB_CUDA_R(cudaGetLastError());
@@ -1324,6 +1370,14 @@ const smb_match* smb_result_inliers(const smb_result* r, size_t i, size_t* count
   }
   if (count) *count = r->tvg[i].inlier_count;
   return r->inliers + r->tvg[i].inlier_start;
+}
+
+int smb_wait_stream(smb_handle* h, void* stream) {
+  if (!h) return SMB_EINVAL;
+  SMB_CUDA(h, cudaSetDevice(h->device));
+  SMB_CUDA(h, cudaEventRecord(h->ev_ext2, static_cast<cudaStream_t>(stream)));
+  SMB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ext2, 0));
+  return SMB_OK;
 }
 
 int smb_alloc_pinned(size_t bytes, void** out) {

@@ -15,7 +15,8 @@
 // solve, score every match); the best of the round goes through the local optimisation (moment matrix accumulated
 // by the whole CTA, its smallest eigenvector by Jacobi rotations) and the trial budget is re-derived from the inlier
 // ratio exactly like RANSAC::ComputeNumTrials -- so the number of samples drawn follows COLMAP's stopping rule in
-// units of 128.  All arithmetic in double, like COLMAP's.
+// units of 128.  Solvers, local optimisation, every adopted model's score and the final inlier mask are computed in
+// double like COLMAP's; only the bulk scoring of the 128 hypotheses of a round is single precision (residual_f).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -168,6 +169,28 @@ __device__ __forceinline__ double transfer_sq(const double* H, double x1, double
 template <bool kIsF>
 __device__ __forceinline__ double residual(const double* M, const float4 p) {
   return kIsF ? sampson_sq(M, p.x, p.y, p.z, p.w) : transfer_sq(M, p.x, p.y, p.z, p.w);
+}
+
+// Single-precision residuals for scoring the minimal-sample hypotheses (128 per round x every match: the bulk of the
+// arithmetic).  Models are rescaled to unit largest entry first; a squared error near the 16 px^2 threshold carries a
+// relative error of ~1e-4 -- a borderline match may flip for a HYPOTHESIS, never for an accepted model: every
+// candidate that beats the best so far is re-scored in double before it is adopted, and so are the local models
+// and the final inlier mask.
+template <bool kIsF>
+__device__ __forceinline__ float residual_f(const float* M, const float4 p) {
+  if (kIsF) {
+    const float Fx0 = M[0] * p.x + M[1] * p.y + M[2], Fx1 = M[3] * p.x + M[4] * p.y + M[5], Fx2 = M[6] * p.x + M[7] * p.y + M[8];
+    const float Ft0 = M[0] * p.z + M[3] * p.w + M[6], Ft1 = M[1] * p.z + M[4] * p.w + M[7];
+    const float e = p.z * Fx0 + p.w * Fx1 + Fx2;
+    const float den = Fx0 * Fx0 + Fx1 * Fx1 + Ft0 * Ft0 + Ft1 * Ft1;
+    return den > 0.f ? e * e / den : 3e38f;
+  } else {
+    const float w = M[6] * p.x + M[7] * p.y + M[8];
+    const float iw = 1.f / w;
+    const float dx = (M[0] * p.x + M[1] * p.y + M[2]) * iw - p.z, dy = (M[3] * p.x + M[4] * p.y + M[5]) * iw - p.w;
+    const float r = dx * dx + dy * dy;
+    return r == r ? r : 3e38f;  // NaN (w == 0) never counts
+  }
 }
 
 // RANSAC::ComputeNumTrials
@@ -451,14 +474,20 @@ __device__ int loransac(Shared& sh, const float4* __restrict__ pts, uint32_t m, 
                         : four_point(pts, reinterpret_cast<const uint32_t(&)[4]>(idx), models);
     int my_cnt = -1, my_k = 0;
     double my_sum = 1e300;
+    const float thr_f = (float)thr;
     for (int k = 0; k < nm; ++k) {
+      double big = 0.0;
+      for (int j = 0; j < 9; ++j) big = fmax(big, fabs(models[k][j]));
+      if (!(big > 0.0)) continue;
+      float fm[9];
+      for (int j = 0; j < 9; ++j) fm[j] = (float)(models[k][j] / big);
       int cnt = 0;
-      double sum = 0.0;
+      float sum = 0.f;
       for (uint32_t i = 0; i < m; ++i) {
-        const double r = residual<kIsF>(models[k], pts[i]);
-        if (r <= thr) { ++cnt; sum += r; }
+        const float r = residual_f<kIsF>(fm, pts[i]);
+        if (r <= thr_f) { ++cnt; sum += r; }
       }
-      if (cnt > my_cnt || (cnt == my_cnt && sum < my_sum)) { my_cnt = cnt; my_sum = sum; my_k = k; }
+      if (cnt > my_cnt || (cnt == my_cnt && (double)sum < my_sum)) { my_cnt = cnt; my_sum = (double)sum; my_k = k; }
     }
     sh.t_cnt[tid] = my_cnt;
     sh.t_sum[tid] = my_sum;
@@ -471,14 +500,23 @@ __device__ int loransac(Shared& sh, const float4* __restrict__ pts, uint32_t m, 
       sh.cand_thread = better ? bt : -1;
     }
     __syncthreads();
-    const int winner = sh.cand_thread;
-    if (winner >= 0) {  // uniform across the CTA
-      if (tid == winner) {
-        for (int k = 0; k < 9; ++k) sh.model[k] = models[my_k][k];
-        sh.best_cnt = my_cnt;
-        sh.best_sum = my_sum;
+    int winner = sh.cand_thread;
+    if (winner >= 0) {  // uniform across the CTA: re-score the round's winner in double before adopting it
+      if (tid == winner)
+        for (int k = 0; k < 9; ++k) sh.cand[k] = models[my_k][k];
+      __syncthreads();
+      score_block<kIsF>(sh, pts, m, sh.cand, thr);
+      const bool adopt = sh.cand_cnt > sh.best_cnt || (sh.cand_cnt == sh.best_cnt && sh.cand_sum < sh.best_sum);
+      __syncthreads();
+      if (adopt && tid == 0) {
+        for (int k = 0; k < 9; ++k) sh.model[k] = sh.cand[k];
+        sh.best_cnt = sh.cand_cnt;
+        sh.best_sum = sh.cand_sum;
       }
       __syncthreads();
+      if (!adopt) winner = -1;
+    }
+    if (winner >= 0) {
       if (sh.best_cnt > kMin && sh.best_cnt >= kLocal) {  // local optimisation on the new best model's inliers
         local_model<kIsF>(sh, pts, m, thr);
         score_block<kIsF>(sh, pts, m, sh.cand, thr);

@@ -113,6 +113,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     L.smb_stream.argtypes = [vp]
     L.smb_stream.restype = vp
     L.smb_stream_wait_uploads.argtypes = [vp, vp]
+    L.smb_wait_stream.argtypes = [vp, vp]
     L.smb_synchronize.argtypes = [vp]
     L.smb_default_tvg_options.argtypes = [ctypes.POINTER(smb_tvg_options)]
     L.smb_default_tvg_options.restype = None
@@ -325,6 +326,10 @@ class SiftMatcher:
     def stream_wait_uploads(self, stream: int) -> None:
         """Make `stream` (a cudaStream_t handle) wait on the device for every upload queued so far."""
         self._check(self._L.smb_stream_wait_uploads(self._h, ctypes.c_void_p(int(stream))))
+
+    def wait_stream(self, stream: int) -> None:
+        """Order the kernels of the match calls that follow behind the work queued so far on `stream`."""
+        self._check(self._L.smb_wait_stream(self._h, ctypes.c_void_p(int(stream))))
 
     def synchronize(self) -> None:
         self._check(self._L.smb_synchronize(self._h))

@@ -334,10 +334,11 @@ def test_full_size_pairs_against_the_oracle(oracle):
     assert total > 3000
 
 
-def test_halo_style_two_sub_batches_at_8192(oracle):
+def test_halo_style_step_at_8192(oracle):
     """The multi-GPU step at full size on one GPU: own images resident, 'halo' images adopted from device buffers a
     side stream is still filling (smb_put_images_device_async, the NVLink path), own images of a second window still
-    crossing PCIe (smb_put_images_async -> a second sub-batch).  A sample of every pair class meets the oracle."""
+    crossing PCIe (smb_put_images_async -> waited for inside the score kernel).  A sample of every pair class meets the
+    oracle."""
     import torch
     ids = list(range(12))
     imgs = [synth.make_image(i, 8192) for i in ids]
@@ -361,13 +362,14 @@ def test_halo_style_two_sub_batches_at_8192(oracle):
                                         num_threads=os.cpu_count())
             for k, w in zip(sample, want):
                 assert np.array_equal(r.matches(k), w), f"pair {tuple(pairs[k])}"
-        assert 1 <= t["sub_batches"] <= 2 and t["score_launches"] == t["sub_batches"]
+        assert t["sub_batches"] == 1 and t["score_launches"] == 1     # one launch: no sub-batch per upload
         m.synchronize()
 
 
 def test_pairs_are_planned_in_upload_landing_order(oracle):
-    """With uploads in flight one call is split into sub-batches per upload ticket and the pairs are taken in
-    the order their images land; the results must still come back per pair in the CALLER's order."""
+    """With host uploads in flight the pairs are taken in the order their images land and the score kernel waits, item
+    by item, for the upload ticket an item depends on (one launch); the results must still come back per pair in
+    the CALLER's order."""
     import torch
     ids = list(range(12))
     imgs = [torch.from_numpy(synth.make_image(i, 2048 + 64 * (i % 5), track_step=128)).pin_memory().numpy() for i in ids]
