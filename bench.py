@@ -398,14 +398,14 @@ def run_headline(cx: Ctx, args):
 
     # ---- end to end through the public API: host (pinned) descriptors in, matches out, every step.
     # The images are uploaded asynchronously in 3-4 chunks (a short first one, so matching can start early) and ONE
-    # match call follows: the library takes the pairs in the order their images land, one sub-batch per upload
-    # ticket, each waiting on the device for its own ticket only -- so the copy of chunk k+1 overlaps the matching of
-    # chunk k without any host round trip in between.  With N > 1 the halo this rank SENDS is its first overlap-1
+    # match call follows: the library takes the pairs in the order their images land and its one score launch waits,
+    # item by item inside the kernel, for the upload an item depends on -- so the copy of chunk k+1 overlaps the
+    # matching of chunk k without any host round trip or extra launch in between.  With N > 1 the halo this rank SENDS is its first overlap-1
     # images: the NCCL send is ordered behind their upload on the device (smb_stream_wait_uploads), not on the host.
     n_own = len(own_ids)
     if world == 1:
-        first = min(n_own, OVERLAP + 6)
-        bounds = sorted(set([0, first, max(first, (2 * n_own) // 5), n_own]))
+        first = min(n_own, 2 * OVERLAP)          # 20 / 30 / 50 images of 100 measured best (tools/e2e_chunks.py)
+        bounds = sorted(set([0, first, max(first, n_own // 2), n_own]))
     else:
         first = min(n_own, OVERLAP + 2)
         bounds = sorted(set([0, first] + [first + ((n_own - first) * c) // 3 for c in (1, 2, 3)]))
@@ -621,7 +621,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(hd["h2d"]), "d2h_bytes_per_step": int(hd["d2h"]),
                     "note": "wall clock around clear_images + put_images_async (pinned host descriptors, 3-4 chunks) + "
                             "halo exchange (N > 1, ordered behind the uploads on the device) + one match call whose "
-                            "sub-batches wait on the device for their own upload; matches land in pinned host memory"},
+                            "score kernel waits per work item for the upload it needs; matches land in pinned host memory"},
             "gpu_launches": int(acc["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "score_tcgen05_kernel",

@@ -25,7 +25,11 @@ abi = len(pairs) * reps / (time.perf_counter() - t0)
 m.close()
 print(json.dumps({"what": "C ABI, pageable descriptors, one put_images + one match_pairs", "pairs_per_s": abi, "pairs": len(pairs), "matches": total}), flush=True)
 
-for packet in (4, 25, 100):
+rng = np.random.default_rng(0)
+kps = [np.concatenate([rng.uniform(0, 4000, size=(n_desc, 2)), np.zeros((n_desc, 4))], axis=1).astype(np.float32) for _ in ids]
+enc = scanner_sim.encode_table(ids, kps, descs)
+for verify, packet in (("none", 4), ("none", 25), ("none", 100), ("gpu", 25), ("gpu", 100)):
+    os.environ["SMB_OP_VERIFY"] = verify      # gpu: two-view verification of every pair (random keypoints: worst case)
     with scanner_sim.OpKernel() as k:
         k.run_table(ids, kps, descs, overlap=overlap, packet_size=packet, decode=False, encoded=enc)   # warm-up
         k.new_stream()
@@ -34,6 +38,6 @@ for packet in (4, 25, 100):
             out_ids, out_tvg = k.run_table(ids, kps, descs, overlap=overlap, packet_size=packet, decode=False, encoded=enc)
             k.new_stream()
         dt = (time.perf_counter() - t0) / reps
-    print(json.dumps({"what": "op through the fake Scanner dispatch", "packet_size": packet, "rows_per_s": n_img / dt,
+    print(json.dumps({"what": "op through the fake Scanner dispatch", "verify": verify, "packet_size": packet, "rows_per_s": n_img / dt,
                       "pairs_per_s": len(pairs) / dt, "ratio_to_c_abi": len(pairs) / dt / abi, "ms_per_table": dt * 1e3,
                       "output_bytes": int(sum(out_tvg))}), flush=True)
