@@ -13,7 +13,8 @@ def T(f, n=10):
 m.put_images(ids, imgs)
 print("match all (resident) %.3f ms" % T(lambda: m.match_pairs_count(pairs)))
 for bounds in ([0, 16, 40, 100], [0, 14, 36, 100], [0, 18, 45, 100], [0, 20, 50, 100], [0, 16, 36, 64, 100], [0, 16, 48, 100],
-               [0, 14, 30, 56, 100], [0, 24, 56, 100]):
+               [0, 14, 30, 56, 100], [0, 24, 56, 100], [0, 8, 20, 44, 100], [0, 4, 12, 28, 56, 100], [0, 6, 14, 30, 60, 100],
+               [0, 12, 30, 60, 100], [0, 10, 20, 40, 70, 100]):
     n = len(bounds) - 1
     groups = [[] for _ in range(n)]
     for a, b in pairs.tolist():
