@@ -323,7 +323,8 @@ __device__ __forceinline__ void insert_loop(ScoreShared* sh, TopTwo* __restrict_
 
 // Second stage of the logged insertion: every survivor that is not the final best of its row (column)
 // competes for that row's (column's) runner-up key.  Keys are distinct, so "not the best" == "key != k1".
-__global__ void __launch_bounds__(256)
+// (128 threads, <= 32 registers: small enough to share an SM with a resident score CTA, see decide_kernel)
+__global__ void __launch_bounds__(128, 16)
 runner_up_kernel(const uint4* __restrict__ entries, const unsigned long long* __restrict__ count,
                  unsigned long long* __restrict__ overflow_flag, unsigned long long capacity, TopTwo* __restrict__ acc) {
   unsigned long long n = *count;
@@ -759,7 +760,12 @@ fetch_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src_
 // =====================================================================================
 // decide: FindBestMatchesOneWay tests + cross-check + ordered compaction, one CTA per pair
 // =====================================================================================
-constexpr int kDecideThreads = 512;
+// Two CTA shapes.  128 threads and <= 32 registers per thread: a score CTA leaves 4,096 registers, ~10 KB of shared
+// memory and 1,664 thread slots of its SM unused, exactly enough for ONE such CTA -- so the runner-up and decide
+// kernels of one sub-batch (second stream) run underneath the score kernel of the next one.  512 threads: for the
+// sub-batch whose decide runs alone (the last one), where more threads per pair hide more latency.
+constexpr int kDecideThreadsSmall = 128;
+constexpr int kDecideThreadsLarge = 512;
 
 // acosf(min(score / 512^2, 1)) through the host-libm table; rows/columns without any surviving
 // score (k1 == 0) never match.  Returns the matched index or -1.
@@ -780,7 +786,8 @@ __device__ __forceinline__ int decide_one(const TopTwo t, uint32_t base_slot, co
 // buffer, no device-to-host copy after the kernel and no host round trip to learn how much to copy.  If the
 // matches of this pair would not fit into `out_cap` entries the pair is skipped and *overflow set: the host then
 // repeats the call with a worst-case sized buffer.
-__global__ void __launch_bounds__(kDecideThreads)
+template <int kDecideThreads>
+__global__ void __launch_bounds__(kDecideThreads, kDecideThreads == kDecideThreadsSmall ? 16 : 1)
 decide_kernel(const PairMeta* __restrict__ pairs, TopTwo* __restrict__ acc, const float* __restrict__ lut,
               float max_ratio, float max_distance, int cross_check, uint2* __restrict__ out /* FeatureMatch */,
               unsigned long long out_cap, unsigned long long* __restrict__ out_total,

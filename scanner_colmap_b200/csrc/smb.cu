@@ -136,7 +136,17 @@ struct smb_handle {
   float max_ratio_f = 0.f, max_distance_f = 0.f;
   Filter filter{};
   std::string err;
-  cudaStream_t stream = nullptr;      // synchronous uploads, accumulator clears, every kernel of a match call
+  cudaStream_t stream = nullptr;      // synchronous uploads, accumulator clears, score kernels
+  cudaStream_t stream_b = nullptr;    // runner-up and decide kernels of sub-batch k, underneath the score kernel of k+1
+  std::vector<cudaEvent_t> chain_ev;  // 2 per sub-batch: scored (main stream), decided (second stream)
+  // A call of >= 256 pairs is cut into `waves` sub-batches so that the delivery of all but the last one's matches hides
+  // under scoring.  Adaptive (SMB_WAVES unset): one sub-batch until a call's exposed tail -- runner-up + decide after
+  // its last score kernel -- exceeded 12 % of the call (several GPUs sharing the host's I/O fabric), then four.  More
+  // sub-batches mean smaller score launches (each pays its own tail: -3 % score-kernel rate at four), so a lone
+  // GPU, whose tail is ~8 %, stays at one.
+  int waves = 1;
+  bool waves_adaptive = true;
+  cudaEvent_t tail_ev[3] = {};        // call start, last score kernel done (main stream), call end (second stream)
   cudaStream_t stream_up = nullptr;   // asynchronous uploads (smb_put_images_async): copy engine under the score kernels
   static constexpr int kUpRing = 64;
   cudaEvent_t up_ev[kUpRing] = {};    // up_ev[t % kUpRing] fires when upload ticket t has landed
@@ -174,9 +184,9 @@ struct smb_handle {
   DevBuf<WorkItem> d_items;
   DevBuf<TopTwo> d_acc;
   size_t acc_zero_slots = 0;  // leading slots of d_acc known to be zero: decide_kernel clears what a sub-batch dirtied
-  static constexpr int kNumCounters = 6;
-  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries, [3] log overflowed,
-                                             // [4] result buffer overflowed
+  static constexpr int kNumCounters = 8;
+  unsigned long long* d_counters = nullptr;  // [0] out_total, [1] candidates, [2] survivor-log entries (log half 0),
+                                             // [3] log overflowed, [4] result buffer overflowed, [5] log entries (half 1)
   DevBuf<uint4> d_log;                       // survivor log (kernels.cuh SurvivorLog)
   DevBuf<unsigned long long> d_cta_busy;     // profiling: per score launch, per CTA busy nanoseconds
   PinnedBuf<unsigned long long> h_cta_busy;
@@ -559,6 +569,10 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SMB_DEBUG_FLAGS")) h->dbg_flags = (uint32_t)strtoul(e, nullptr, 0);
   if (const char* e = getenv("SMB_LOG_CAP")) h->log_cap = (size_t)strtoull(e, nullptr, 0);
+  if (const char* e = getenv("SMB_WAVES")) {
+    h->waves = std::max(1, atoi(e));
+    h->waves_adaptive = false;
+  }
   if (const char* e = getenv("SMB_RESULT_CAP")) h->result_cap_override = (size_t)strtoull(e, nullptr, 0);
   if (const char* e = getenv("SMB_ACC_BUDGET")) h->acc_budget = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 0));  // tests: force sub-batches
   int rc = SMB_OK;
@@ -577,10 +591,12 @@ int smb_create(int cuda_device, const smb_options* opts, smb_handle** out) {
   } while (0)
   SMB_CUDA_C(cudaSetDevice(cuda_device));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking));
   SMB_CUDA_C(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
   for (auto& e : h->up_ev) SMB_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
   SMB_CUDA_C(cudaEventCreateWithFlags(&h->ev_ext2, cudaEventDisableTiming));
+  for (auto& e : h->tail_ev) SMB_CUDA_C(cudaEventCreate(&e));
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -618,7 +634,9 @@ void smb_destroy(smb_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_b) cudaStreamSynchronize(h->stream_b);
   if (h->stream_up) cudaStreamSynchronize(h->stream_up);
+  for (cudaEvent_t e : h->chain_ev) cudaEventDestroy(e);
   if (h->inflight) destroy_result(h->inflight);  // begun and never waited for: the stream is idle now
   for (smb_result* r : h->result_pool) destroy_result(r);
   h->d_pairs.release();
@@ -637,11 +655,14 @@ void smb_destroy(smb_handle* h) {
   if (h->kp_pool) cudaFree(h->kp_pool);
   h->d_pts.release();
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream_b) cudaStreamDestroy(h->stream_b);
   if (h->stream_up) cudaStreamDestroy(h->stream_up);
   for (auto& e : h->up_ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   if (h->ev_ext2) cudaEventDestroy(h->ev_ext2);
+  for (auto& e : h->tail_ev)
+    if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -798,7 +819,11 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   std::vector<Sub> subs;
   std::vector<PairMeta>& pm = h->plan_pairs;
   std::vector<WorkItem>& wi = h->plan_items;
-  const size_t sub_budget = h->acc_budget;
+  // Two accumulator regions ping-pong between consecutive sub-batches (the decide of k runs under the score of k+1),
+  // so a sub-batch may use half the budget; a call of >= 64 pairs is cut into `waves` sub-batches of equal pair count
+  // so that only the last one's runner-up / decide (1 / waves of the result delivery) is exposed.
+  const size_t sub_budget = std::max<size_t>(h->acc_budget / 2, 1);
+  const size_t wave_pairs = npairs >= 256 && h->waves > 1 ? (npairs + h->waves - 1) / h->waves : npairs;
   size_t out_cap = 0, max_acc = 0;
   uint64_t ops = 0;
   auto is_host_ticket = [&](uint64_t t) { return t > h->up_synced && !h->up_fast[t % smb_handle::kUpRing]; };
@@ -809,7 +834,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
 #endif
   bool pending_host = false;
   for (uint64_t t = h->up_synced + 1; t <= h->up_issued; ++t) pending_host = pending_host || !h->up_fast[t % smb_handle::kUpRing];
-  const bool reuse = h->plan_epoch == h->layout_epoch && !pending_host && h->plan_acc_budget == sub_budget &&
+  const bool reuse = h->plan_epoch == h->layout_epoch && !pending_host && h->plan_acc_budget == sub_budget + (size_t)h->waves &&
                      h->plan_keys.size() == 2 * npairs && h->dev_plan_pairs == npairs && h->dev_plan_items == wi.size() &&
                      std::memcmp(h->plan_keys.data(), keys, 2 * npairs * sizeof(uint64_t)) == 0;
   if (reuse) {
@@ -876,7 +901,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       // Pending HOST uploads are waited for inside the score kernel, item by item (WorkItem::wait_ticket); with the
       // test engine, which has no such wait, they split the call like the accumulator budget does.
       const bool newer_upload = !kernel_waits && host_ticket > cur.split_ticket;
-      if (p > cur.first && (cur.acc + need > sub_budget || newer_upload)) {
+      if (p > cur.first && (cur.acc + need > sub_budget || newer_upload || p - cur.first >= wave_pairs)) {
         cur.last = p;
         subs.push_back(cur);
         cur = Sub{p, 0, wi.size(), 0, 0, cur.split_ticket, cur.wait_ticket};
@@ -946,13 +971,13 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
     h->plan_out_cap = out_cap;
     h->plan_max_acc = max_acc;
     h->plan_ops = ops;
-    h->plan_acc_budget = sub_budget;
+    h->plan_acc_budget = sub_budget + (size_t)h->waves;
     h->plan_epoch = h->layout_epoch;   // (the device copy of the plan is made below)
   }
   }  // !reuse
   res->worst_case = out_cap;
   const size_t n_items_total = wi.size();
-  const size_t acc_region = (max_acc + 15) / 16 * 16;
+  const size_t acc_region = (max_acc + 15) / 16 * 16;  // region 1 starts here (region 0 at 0)
   use_log = use_log && h->log_cap;
 #ifdef SMB_TEST_ENGINES
   use_log = use_log && h->opts.engine == SMB_ENGINE_TCGEN05;
@@ -969,14 +994,20 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   if (!reserve_pinned(&res->matches, &res->matches_cap, matches_want) || !reserve_pinned(&res->pair_out, &res->pair_cap, npairs))
     return fail(h, SMB_ENOMEM, "pinned result allocation failed (%zu matches, %zu pairs)", matches_want, npairs);
   if (cudaSuccess != h->d_pairs.reserve(npairs) || cudaSuccess != h->d_items.reserve(std::max<size_t>(n_items_total, 1)) ||
-      cudaSuccess != reserve_acc(h, std::max<size_t>(acc_region, 1)) || cudaSuccess != h->h_pairs.reserve(npairs) ||
+      cudaSuccess != reserve_acc(h, std::max<size_t>((subs.size() > 1 ? 2 : 1) * acc_region, 1)) ||
+      cudaSuccess != h->h_pairs.reserve(npairs) ||
       cudaSuccess != h->h_items.reserve(std::max<size_t>(n_items_total, 1)) ||
       (use_log && cudaSuccess != h->d_log.reserve(h->log_cap))) {
     cudaGetLastError();
     return fail(h, SMB_ENOMEM, "device/pinned scratch allocation failed (pairs=%zu acc=%zu)", npairs, acc_region);
   }
+  while (h->chain_ev.size() < 2 * subs.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(h, SMB_ECUDA, "cudaEventCreate failed");
+    h->chain_ev.push_back(e);
+  }
   if (prof) {
-    while (res->ev.size() < 4 * subs.size() + 2) {
+    while (res->ev.size() < 5 * subs.size() + 2) {
       cudaEvent_t e;
       if (cudaEventCreate(&e) != cudaSuccess) return fail(h, SMB_ECUDA, "cudaEventCreate failed");
       res->ev.push_back(e);
@@ -993,12 +1024,13 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
   res->ops = ops;
   res->launches = res->score_launches = res->plan_uploaded = 0;
 
-  cudaStream_t st = h->stream;
+  cudaStream_t st = h->stream, sb2 = h->stream_b;
 #define SMB_CUDA_R(expr)                                                                         \
   do {                                                                                           \
     cudaError_t e__ = (expr);                                                                    \
     if (e__ != cudaSuccess) {                                                                    \
       cudaStreamSynchronize(st);                                                                 \
+      cudaStreamSynchronize(sb2);                                                                \
       h->acc_zero_slots = 0; /* kernels may have dirtied accumulators no decide_kernel cleared */  \
       return fail(h, SMB_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     }                                                                                            \
@@ -1012,6 +1044,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
                                    (n_items_total == 0 ||
                                     std::memcmp(h->h_items.p, wi.data(), n_items_total * sizeof(WorkItem)) == 0));
   if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[0], st));
+  SMB_CUDA_R(cudaEventRecord(h->tail_ev[0], st));
   SMB_CUDA_R(cudaMemsetAsync(h->d_counters, 0, smb_handle::kNumCounters * sizeof(unsigned long long), st));
   if (!same_plan) {
     h->dev_plan_pairs = h->dev_plan_items = 0;  // invalid until the fetch below has been queued
@@ -1030,23 +1063,35 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
     h->dev_plan_pairs = npairs;
     h->dev_plan_items = n_items_total;
   }
-  const SurvivorLog slog{use_log ? h->d_log.p : nullptr, h->d_counters + 2, (unsigned long long)h->log_cap};
   if (n_items_total && !h->tmap_valid) return fail(h, SMB_ECUDA, "descriptor pool tensor map is not initialised");
 
+  // ---- the sub-batches, software-pipelined over two streams:
+  //   main stream   : score(0)   score(1)              score(2)              ...
+  //   second stream :            runner-up(0) decide(0) runner-up(1) decide(1) ...
+  // Consecutive sub-batches alternate between two accumulator regions and the two halves of the survivor log;
+  // score(k) waits for decide(k - 2), which frees its region and log half.  The runner-up and decide CTAs are small
+  // enough to be resident next to a score CTA (kernels.cuh), so the PCIe-bound delivery of sub-batch k's matches
+  // hides under the scoring of k + 1 and only the last sub-batch's is exposed.
+  const size_t log_half = subs.size() > 1 ? h->log_cap / 2 : h->log_cap;
   uint64_t waited = h->up_synced;
   for (size_t k = 0; k < subs.size(); ++k) {
     const Sub& sb = subs[k];
-    TopTwo* acc = h->d_acc.p;  // reused by every sub-batch: all kernels touching it are ordered on the stream
+    const size_t r = k & 1;
+    TopTwo* acc = h->d_acc.p + r * acc_region;
+    const SurvivorLog slog{use_log ? h->d_log.p + r * log_half : nullptr, h->d_counters + (r ? 5 : 2), (unsigned long long)log_half};
+    cudaEvent_t ev_scored = h->chain_ev[2 * k], ev_decided = h->chain_ev[2 * k + 1];
+    if (k >= 2) SMB_CUDA_R(cudaStreamWaitEvent(st, h->chain_ev[2 * (k - 2) + 1], 0));  // region r and log half r are free
     // tickets complete in order on the upload stream: waiting for the newest one this sub-batch needs is enough
     if (sb.wait_ticket > waited) {
       SMB_CUDA_R(cudaStreamWaitEvent(st, h->up_ev[sb.wait_ticket % smb_handle::kUpRing], 0));
       waited = sb.wait_ticket;
     }
-    if (sb.acc > h->acc_zero_slots) {  // only the part no earlier decide_kernel has left clean
-      SMB_CUDA_R(cudaMemsetAsync(acc + h->acc_zero_slots, 0, (sb.acc - h->acc_zero_slots) * sizeof(TopTwo), st));
-      h->acc_zero_slots = sb.acc;
+    if (r * acc_region + sb.acc > h->acc_zero_slots) {  // only what no earlier decide_kernel has left clean: the whole
+      const size_t upto = r * acc_region + sb.acc;       // prefix [0, acc_zero_slots) of d_acc is zero between calls
+      SMB_CUDA_R(cudaMemsetAsync(h->d_acc.p + h->acc_zero_slots, 0, (upto - h->acc_zero_slots) * sizeof(TopTwo), st));
+      h->acc_zero_slots = upto;
     }
-    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[2 + 4 * k], st));
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[2 + 5 * k], st));
     if (sb.items) {
       res->sub_has_items[k] = 1;
       unsigned long long* cand = prof ? h->d_counters + 1 : nullptr;
@@ -1058,7 +1103,7 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       } else
 #endif
       {
-        if (use_log) SMB_CUDA_R(cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned long long), st));
+        if (use_log) SMB_CUDA_R(cudaMemsetAsync(slog.count, 0, sizeof(unsigned long long), st));
         const unsigned grid = (unsigned)std::min<size_t>(sb.items, (size_t)h->num_sms);  // persistent CTAs
         score_tcgen05_kernel<<<grid, kScoreThreads, kScoreSmemBytes, st>>>(h->tmap, h->d_items.p + sb.item0, (uint32_t)sb.items,
                                                                           h->d_pairs.p + sb.first, acc, slog,
@@ -1071,28 +1116,41 @@ static int enqueue_match(smb_handle* h, smb_result* res, bool use_log, size_t ma
       res->score_launches++;
       res->launches++;
     }
-    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[3 + 4 * k], st));
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[3 + 5 * k], st));
+    if (k + 1 == subs.size()) SMB_CUDA_R(cudaEventRecord(h->tail_ev[1], st));
+    SMB_CUDA_R(cudaEventRecord(ev_scored, st));
+    // ---- second stream
+    SMB_CUDA_R(cudaStreamWaitEvent(sb2, ev_scored, 0));
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[4 + 5 * k], sb2));
     if (sb.items && use_log) {
-      runner_up_kernel<<<(unsigned)h->num_sms * 8, 256, 0, st>>>(h->d_log.p, h->d_counters + 2, h->d_counters + 3,
-                                                                (unsigned long long)h->log_cap, acc);
+      runner_up_kernel<<<(unsigned)h->num_sms * 16, 128, 0, sb2>>>(slog.entries, slog.count, h->d_counters + 3, slog.capacity, acc);
       SMB_CUDA_R(cudaGetLastError());
       res->launches++;
     }
-    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[4 + 4 * k], st));
-    decide_kernel<<<(unsigned)(sb.last - sb.first), kDecideThreads, 0, st>>>(
-        h->d_pairs.p + sb.first, acc, h->lut_dev, h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
-        reinterpret_cast<uint2*>(res->matches), (unsigned long long)res->matches_limit, h->d_counters, h->d_counters + 4,
-        res->pair_out);
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[5 + 5 * k], sb2));
+    if (k + 1 < subs.size())  // runs underneath the next sub-batch's score kernel: the small CTA shape
+      decide_kernel<kDecideThreadsSmall><<<(unsigned)(sb.last - sb.first), kDecideThreadsSmall, 0, sb2>>>(
+          h->d_pairs.p + sb.first, acc, h->lut_dev, h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
+          reinterpret_cast<uint2*>(res->matches), (unsigned long long)res->matches_limit, h->d_counters, h->d_counters + 4,
+          res->pair_out);
+    else                      // runs alone
+      decide_kernel<kDecideThreadsLarge><<<(unsigned)(sb.last - sb.first), kDecideThreadsLarge, 0, sb2>>>(
+          h->d_pairs.p + sb.first, acc, h->lut_dev, h->max_ratio_f, h->max_distance_f, cc ? 1 : 0,
+          reinterpret_cast<uint2*>(res->matches), (unsigned long long)res->matches_limit, h->d_counters, h->d_counters + 4,
+          res->pair_out);
     SMB_CUDA_R(cudaGetLastError());
     res->launches++;
-    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[5 + 4 * k], st));
+    if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[6 + 5 * k], sb2));
+    SMB_CUDA_R(cudaEventRecord(ev_decided, sb2));
   }
+  // the second stream has seen every score kernel and ran every decide: the counters (and profiling data) last
   SMB_CUDA_R(cudaMemcpyAsync(res->counters, h->d_counters, smb_handle::kNumCounters * sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, st));
+                             cudaMemcpyDeviceToHost, sb2));
   if (prof)
     SMB_CUDA_R(cudaMemcpyAsync(h->h_cta_busy.p, h->d_cta_busy.p, subs.size() * (size_t)h->num_sms * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, st));
-  if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[1], st));
+                               cudaMemcpyDeviceToHost, sb2));
+  if (prof) SMB_CUDA_R(cudaEventRecord(res->ev[1], sb2));
+  SMB_CUDA_R(cudaEventRecord(h->tail_ev[2], sb2));
 #undef SMB_CUDA_R
   return SMB_OK;
 }
@@ -1114,7 +1172,8 @@ static void flush_pending_free(smb_handle* h) {
 // or the matches did not fit the result buffer (repeat with the worst-case size).
 static int finish_match(smb_handle* h, smb_result* res) {
   for (int attempt = 0;; ++attempt) {
-    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream_b);  // the call's last work is on the second stream
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
       h->acc_zero_slots = 0;
       return fail(h, SMB_ECUDA, "match call failed on the device: %s", cudaGetErrorString(e));
@@ -1127,6 +1186,13 @@ static int finish_match(smb_handle* h, smb_result* res) {
     if (rc != SMB_OK) return rc;
   }
   res->total = (size_t)res->counters[0];
+  if (h->waves_adaptive && h->waves == 1 && res->npairs >= 256) {
+    float call_ms = 0.f, tail_ms = 0.f;
+    if (cudaEventElapsedTime(&call_ms, h->tail_ev[0], h->tail_ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&tail_ms, h->tail_ev[1], h->tail_ev[2]) == cudaSuccess && tail_ms > 0.12f * call_ms)
+      h->waves = 4;
+    cudaGetLastError();
+  }
   if (res->npairs) h->matches_per_pair = std::max(h->matches_per_pair, (double)res->total / (double)res->npairs);
   std::memset(&h->timing, 0, sizeof h->timing);
   h->timing.ops = res->ops;
@@ -1134,13 +1200,13 @@ static int finish_match(smb_handle* h, smb_result* res) {
   h->timing.total_launches = res->launches;
   h->timing.sub_batches = (uint32_t)res->n_subs;
   h->timing.plan_uploaded = res->plan_uploaded;
-  if (h->opts.profile && res->ev.size() >= 4 * res->n_subs + 2) {
+  if (h->opts.profile && res->ev.size() >= 5 * res->n_subs + 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, res->ev[0], res->ev[1]) == cudaSuccess) h->timing.total_ms = ms;
-    for (size_t k = 0; k < res->n_subs; ++k) {
-      if (cudaEventElapsedTime(&ms, res->ev[2 + 4 * k], res->ev[3 + 4 * k]) == cudaSuccess) h->timing.score_ms += ms;
-      if (cudaEventElapsedTime(&ms, res->ev[3 + 4 * k], res->ev[4 + 4 * k]) == cudaSuccess) h->timing.runner_up_ms += ms;
-      if (cudaEventElapsedTime(&ms, res->ev[4 + 4 * k], res->ev[5 + 4 * k]) == cudaSuccess) h->timing.decide_ms += ms;
+    for (size_t k = 0; k < res->n_subs; ++k) {  // (runner-up / decide of sub-batch k overlap the score kernel of k + 1)
+      if (cudaEventElapsedTime(&ms, res->ev[2 + 5 * k], res->ev[3 + 5 * k]) == cudaSuccess) h->timing.score_ms += ms;
+      if (cudaEventElapsedTime(&ms, res->ev[4 + 5 * k], res->ev[5 + 5 * k]) == cudaSuccess) h->timing.runner_up_ms += ms;
+      if (cudaEventElapsedTime(&ms, res->ev[5 + 5 * k], res->ev[6 + 5 * k]) == cudaSuccess) h->timing.decide_ms += ms;
     }
     cudaGetLastError();
     h->timing.candidates = res->counters[1];
@@ -1177,6 +1243,7 @@ static int begin_keys(smb_handle* h, std::vector<uint64_t>&& keys, size_t npairs
   int rc = enqueue_match(h, res, /*use_log=*/true, /*matches_want=*/0);
   if (rc != SMB_OK) {
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream_b);
     h->result_pool.push_back(res);
     return rc;
   }
@@ -1424,6 +1491,7 @@ int smb_synchronize(smb_handle* h) {
   if (!h) return SMB_EINVAL;
   SMB_CUDA(h, cudaSetDevice(h->device));
   SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  SMB_CUDA(h, cudaStreamSynchronize(h->stream_b));
   return drain_uploads(h);
 }
 

@@ -18,6 +18,6 @@ for prof in (True, False):
     t = m.timing()
     print(f"profile={prof}: wall {np.median(walls):.3f} ms (begin returns after {np.median(begins):.3f} ms) | device total {t['total_ms']:.3f} "
           f"score {t['score_ms']:.3f} runner_up {t['runner_up_ms']:.3f} decide {t['decide_ms']:.3f} "
-          f"-> other device {t['total_ms'] - t['score_ms'] - t['runner_up_ms'] - t['decide_ms']:.3f} | launches {t['total_launches']} "
+          f"-> total - score {t['total_ms'] - t['score_ms']:.3f} | sub-batches {t['sub_batches']} launches {t['total_launches']} "
           f"plan_uploaded {t['plan_uploaded']}", flush=True)
     m.close()
