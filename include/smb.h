@@ -77,8 +77,9 @@ typedef struct smb_result smb_result;
 typedef struct smb_timing {
   float total_ms;       /* first kernel of the call to the last one (results are in host memory when it ends) */
   float score_ms;       /* score_tcgen05_kernel only, summed over the call's sub-batches */
-  float runner_up_ms;   /* runner_up_kernel, summed */
-  float decide_ms;      /* decide_kernel (writes the matches straight into pinned host memory), summed */
+  float runner_up_ms;   /* runner_up_kernel, summed (kernel time: with several sub-batches these two run on a second */
+  float decide_ms;      /* stream underneath the next sub-batch's score kernel); decide_kernel writes the matches
+                           straight into pinned host memory */
   uint32_t score_launches;
   uint32_t total_launches; /* every kernel of this library launched by the call */
   uint32_t sub_batches;

@@ -252,6 +252,26 @@ def test_accumulator_budget_forces_sub_batches(oracle, monkeypatch):
     assert total > 300
 
 
+@pytest.mark.parametrize("waves", ["4", "7"])
+def test_waves_pipelined_over_two_streams_are_invisible(oracle, monkeypatch, waves):
+    """A call of >= 256 pairs cut into waves: runner-up / decide of wave k run on a second stream underneath the score
+    kernel of wave k+1, on alternating accumulator regions and survivor-log halves (chosen adaptively when the
+    delivery tail is long; SMB_WAVES forces it).  Per-pair results must not change."""
+    ids = list(range(30))
+    imgs = [synth.make_image(i, 600 + 31 * (i % 9), track_step=32) for i in ids]
+    pairs = sequential_pairs(ids, 12)
+    assert len(pairs) >= 256
+    monkeypatch.setenv("SMB_WAVES", waves)
+    with SiftMatcher(profile=True) as m:
+        m.put_images(ids, imgs)
+        total = _check_pairs(oracle, m, imgs, ids, pairs)
+        t = m.timing()
+        assert t["sub_batches"] == int(waves) and t["score_launches"] == int(waves)
+        total2 = _check_pairs(oracle, m, imgs, ids, pairs)          # plan reused, regions clean again
+        assert m.timing()["plan_uploaded"] == 0
+    assert total == total2 > 2000
+
+
 def test_result_buffer_overflow_is_repeated_exactly(oracle, monkeypatch):
     """decide_kernel writes matches straight into pinned host memory sized from earlier calls; if they do not fit,
     the call is repeated with a worst-case sized buffer (SMB_RESULT_CAP forces a tiny first attempt)."""
