@@ -88,7 +88,7 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 //   warp 0        TMA producer: A strip (2 x 128 rows, kept for the whole item) + ring of B tiles (256 rows)
 //   warp 1        MMA issuer: per B tile two accumulator tiles (strip rows 0-127 / 128-255), 4 x K32 each,
 //                 ping-pong between the two 256-column halves of TMEM
-//   warps 4-11    filter epilogue: tcgen05.ld + 3-input max tree over each thread's four 32-column runs;
+//   warps 4-11    filter epilogue: two tcgen05.ld.x64 + 3-input max tree over each thread's four 32-column runs;
 //                 the accumulator buffer is released as soon as it has been read.  A run whose maximum
 //                 reaches min_score is copied, exact scores and all, from registers to a shared-memory
 //                 mailbox (a few vector stores; rare).
@@ -96,13 +96,16 @@ __device__ __forceinline__ void top2_insert2(TopTwo* __restrict__ acc, uint32_t 
 //                 keys with fire-and-forget RED.MAX and are appended to a survivor log, from which
 //                 runner_up_kernel settles the second-best keys afterwards.
 //
-// Where the time goes (build with -DSMB_TRACE, run tools/trace_case.py): the kernel is bound by the epilogue
-// warps' serial per-tile chain -- barrier wait (~150 clk even when complete: every shared-memory access
-// queues behind the MMA operand reads), tcgen05.ld (~165), then the max trees of the two warps that share an
-// SMSP's ALU pipe (~300) -- not by the tensor pipe (512 clk per tile), and each survivor run a warp posts
-// costs it another ~400 clk of shared-memory stores.  Variants built and measured slower: cta_group::2 CTA
-// pairs, 16 epilogue warps, two MMA issuer threads with setmaxnreg warpgroups, N = 160 x 3 / N = 128 x 4
-// TMEM buffers (DESIGN.md "Kernel history").
+// Where the time goes (build with -DSMB_TRACE, run tools/trace_case.py; microbenchmarks tools/smem_port.cu,
+// tools/mbar_probe.cu): the kernel is bound by the epilogue warps' serial per-tile chain -- barrier wait (a try_wait
+// on a complete mbarrier answers in ~58 clk, with a suspend hint in ~86), two tcgen05.ld.x64 (~170 until the buffer
+// is handed back), then the max trees of the two warps that share an SMSP's ALU pipe (~230) -- not by the tensor
+// pipe (538 clk per tile with these operand addresses, measured in isolation; concurrent TMA / TMEM-read / mailbox
+// traffic does not slow it), and by survivor posting: without it the same kernel runs at 4.07 POP/s, with it at
+// 3.31 (one warp posting delays the release of its next tile, and one of the eight posts in 85 % of the tiles).
+// Variants built and measured slower: cta_group::2 CTA pairs, 16 epilogue warps, two MMA issuer threads with
+// setmaxnreg warpgroups, N = 160 x 3 / N = 128 x 4 TMEM buffers, thin records + dp4a recomputation by the insert
+// warps, a pre-filter split between the ALU and FMA pipes.
 // =====================================================================================
 constexpr int kStages = 4;                     // B-tile ring
 constexpr int kAStages = 2;                    // A-strip ring (next item's strip prefetched)
@@ -534,7 +537,10 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
 #ifdef SMB_TRACE
           const uint32_t tr0 = tr_clock();
 #endif
-          ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
+          // The accumulator is usually complete long before this warp asks.  A plain try_wait answers in ~58 clk, the
+          // one with a suspend-time hint inside mbar_wait in ~86 (tools/mbar_probe.cu): ask plainly once first.
+          // (+3 % on the whole kernel; the same on the MMA / TMA threads' waits, which usually do have to wait, costs 1 %.)
+          if (!ptx::mbar_try_wait(ptx::smem_u32(&sh->t_full[ts]), tph)) ptx::mbar_wait(ptx::smem_u32(&sh->t_full[ts]), tph);
           ptx::tcgen05_fence_after();
 #ifdef SMB_TRACE
           const uint32_t tr1 = tr_clock();
@@ -542,12 +548,13 @@ score_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem* _
           ++tr_tiles;
 #endif
           const uint32_t taddr = tmem_base + lane_addr + ts * kTileCols + col0;
-          uint32_t v0[32], v1[32], v2[32], v3[32];  // all runs in flight; ptxas tracks each load's registers
-          ptx::tmem_ld_32x32b_x32(taddr, v0);
-          ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
+          uint32_t v0[32], v1[32], v2[32], v3[32];  // the warp's 128 columns of the tile: 128 registers per thread
           if constexpr (kRunsPerWarp == 4) {
-            ptx::tmem_ld_32x32b_x32(taddr + 2 * kRunCols, v2);
-            ptx::tmem_ld_32x32b_x32(taddr + 3 * kRunCols, v3);
+            ptx::tmem_ld_32x32b_x64(taddr, v0, v1);
+            ptx::tmem_ld_32x32b_x64(taddr + 2 * kRunCols, v2, v3);
+          } else {
+            ptx::tmem_ld_32x32b_x32(taddr, v0);
+            ptx::tmem_ld_32x32b_x32(taddr + kRunCols, v1);
           }
           ptx::tmem_wait_ld();
 #ifdef SMB_TRACE

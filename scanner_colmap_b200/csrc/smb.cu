@@ -399,11 +399,6 @@ int drain_uploads(smb_handle* h) {
   return SMB_OK;
 }
 
-// Give an image's pool rows back.  No device synchronisation: every kernel that could read them belongs to a match
-// call, and a match call has either completed (smb_match_pairs / smb_result_wait return after the stream has been
-// synchronised) or is the one call in flight, in which case the rows are parked until its wait.  Copies into
-// recycled rows are ordered behind earlier work of the stream they are queued on; only an upload that is still
-// in flight INTO these rows on the upload stream has to be waited for.
 void poll_uploads(smb_handle* h) {  // tickets whose event has fired need no waiting any more
   while (h->up_synced < h->up_issued && (h->up_open == 0 || h->up_synced + 1 < h->up_open) &&
          cudaEventQuery(h->up_ev[(h->up_synced + 1) % smb_handle::kUpRing]) == cudaSuccess)
@@ -411,6 +406,11 @@ void poll_uploads(smb_handle* h) {  // tickets whose event has fired need no wai
   cudaGetLastError();  // cudaErrorNotReady from the query is not an error
 }
 
+// Give an image's pool rows back.  No device synchronisation: every kernel that could read them belongs to a match
+// call, and a match call has either completed (smb_match_pairs / smb_result_wait return after both streams have been
+// synchronised) or is the one call in flight, in which case the rows are parked until its wait.  Copies into
+// recycled rows are ordered behind earlier work of the stream they are queued on; only an upload that is still
+// in flight INTO these rows on the upload stream has to be waited for.
 int retire_rows(smb_handle* h, const ImageEntry& e) {
   if (e.up_seq > h->up_synced) poll_uploads(h);
   if (e.up_seq > h->up_synced)

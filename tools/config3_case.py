@@ -11,7 +11,7 @@ print(f"generated {n} images in {time.time()-t0:.1f}s", flush=True)
 ids = list(range(n)); pairs = sequential_pairs(ids, 20)
 m = SiftMatcher(profile=True); m.put_images(ids, imgs)
 for _ in range(2):
-    t0 = time.perf_counter(); res = m.match_pairs(pairs, copy=False) if False else None; tot = m.match_pairs_count(pairs); wall = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); tot = m.match_pairs_count(pairs); wall = (time.perf_counter() - t0) * 1e3
     t = m.timing()
     print(f"{len(pairs)} pairs: wall={wall:.1f}ms ({len(pairs)/wall*1e3:.0f} pairs/s) score={t['score_ms']:.1f}ms launches={t['score_launches']} "
           f"TOPS={t['ops']/t['score_ms']/1e9:.0f} matches={tot}", flush=True)

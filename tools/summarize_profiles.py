@@ -8,18 +8,21 @@ for r in rows:
     name = r[4].split('(')[0]; t = float(r[-1])
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += t
 tot = sum(v[1] for v in agg.values())
-ours = sum(v[1] for k, v in agg.items() if k.startswith('smb::'))
+ours = sum(v[1] for k, v in agg.items() if 'smb::' in k)
 lines = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 ({cmd})",
          "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes",
          "# share_of_library = share among this library's kernels (the rest is torch: L2 flush fills, int8 GEMM peak probe, RNG)",
          "kernel,launches,total_ns,share_of_all,share_of_library"]
 for k, v in agg.items():
-    lines.append(f"{k[:110]},{v[0]},{v[1]:.0f},{v[1]/tot:.4f},{(v[1]/ours if k.startswith('smb::') else 0):.4f}")
+    lines.append(f"{k[:110]},{v[0]},{v[1]:.0f},{v[1]/tot:.4f},{(v[1]/ours if 'smb::' in k else 0):.4f}")
 open(f'profiles/{tag}_launches_summary.csv', 'w').write("\n".join(lines) + "\n"); print("\n".join(lines))
 shutil.copy(f'gpurun_out/{tag}_launches.csv', f'profiles/{tag}_launches.csv')
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
-        'sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg', 'sm__cycles_active.avg', 'launch__registers_per_thread',
+        'sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.avg.per_second',
+        'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'sm__cycles_active.avg', 'launch__registers_per_thread',
         'lts__t_sector_hit_rate.pct', 'sm__inst_executed_pipe_alu_realtime.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
         'launch__grid_size', 'launch__block_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed', 'launch__shared_mem_per_block_dynamic', 'lts__t_bytes.sum',
