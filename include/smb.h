@@ -167,11 +167,19 @@ int smb_get_timing(const smb_handle* h, smb_timing* t);
  * verifyTwoViewGeometry -> colmap::TwoViewGeometry::Estimate, sequential_matching.cc:84-101,157-178, which with the
  * reference's dummy cameras is the uncalibrated F / H LORANSAC path).  Statistical contract, not bit parity: COLMAP
  * samples from a thread-local PRNG (DESIGN.md "Two-view geometry"). */
+/* smb_tvg_options.flags.  COLMAP's TwoViewGeometry::Options has detect_watermark = true (a geometry whose inliers are
+ * one pure image translation is reported as WATERMARK; with the reference's default-constructed cameras,
+ * sequential_matching.cc:89, the border-region condition holds for every inlier) -- so detection is ON unless the
+ * first bit is set.  The second bit selects TwoViewGeometry::EstimateMultiple (siftMatchingArgs.multiple_models,
+ * colmap.proto:45, sequential_matching.cc:94-96): estimate, remove the inliers, repeat until DEGENERATE; watermark
+ * models are skipped (multiple_ignore_watermark = true); several models -> config MULTIPLE with all inlier matches. */
+#define SMB_TVG_NO_WATERMARK 1
+#define SMB_TVG_MULTIPLE_MODELS 2
 typedef struct smb_tvg_options {
   int32_t min_num_inliers; /* colmap.proto:41 default 15 */
   int32_t min_num_trials;  /* colmap.proto:32 default 30 */
   int32_t max_num_trials;  /* colmap.proto:33 default 10000 */
-  int32_t pad_;
+  int32_t flags;           /* SMB_TVG_* bits, default 0 */
   double max_error;        /* colmap.proto:26 default 4.0 (pixels) */
   double confidence;       /* colmap.proto:29 default 0.999 */
   double min_inlier_ratio; /* colmap.proto:37 default 0.25 */
@@ -181,7 +189,8 @@ typedef struct smb_tvg_options {
 void smb_default_tvg_options(smb_tvg_options* o);
 
 typedef struct smb_tvg {
-  int32_t config;           /* colmap::TwoViewGeometry::ConfigurationType: 1 DEGENERATE, 3 UNCALIBRATED, 6 PLANAR_OR_PANORAMIC */
+  int32_t config;           /* colmap::TwoViewGeometry::ConfigurationType: 1 DEGENERATE, 3 UNCALIBRATED, 6 PLANAR_OR_PANORAMIC,
+                             * 7 WATERMARK, 8 MULTIPLE (F and H are zero then, as COLMAP leaves them) */
   int32_t num_inliers_f, num_inliers_h;
   int32_t trials_f, trials_h;
   uint32_t inlier_start, inlier_count; /* internal offsets; use smb_result_inliers */

@@ -15,6 +15,14 @@ With cameras that have no prior focal length COLMAP 3.5's TwoViewGeometry::Estim
     DEGENERATE if neither succeeded or both have < min_num_inliers inliers
     config = PLANAR_OR_PANORAMIC if inliers(H) / inliers(F) > max_H_inlier_ratio (0.8) else UNCALIBRATED
     inlier_matches = the matches inside the F model's inlier mask
+    config = WATERMARK if DetectWatermark(...) (Options::detect_watermark, default true): at least
+             watermark_min_inlier_ratio (0.7) of the inliers lie in the border region AND fit one pure image translation
+             (LORANSAC<TranslationTransformEstimator<2>> with min_inlier_ratio = 0.7).  With the reference's dummy
+             cameras (width = height = 0, :89) the "inner" box is the single point (0, 0): every inlier counts as border,
+             so only the translational test decides -- a pair whose inliers are one image shift is reported WATERMARK.
+    multiple_models (colmap.proto:45, default false) selects EstimateMultiple instead: Estimate on the matches, remove
+             the inliers, repeat until DEGENERATE; watermark models are skipped (multiple_ignore_watermark, default
+             true); none -> DEGENERATE, one -> that geometry, several -> config MULTIPLE with all inlier matches.
 
 [ext]: COLMAP is not vendored in the reference and not installable here; the algorithm below is
 restated from the published COLMAP 3.5 sources (src/estimators/two_view_geometry.cc, src/optim/loransac.h,
@@ -48,6 +56,9 @@ class Options:
     min_inlier_ratio: float = 0.25
     max_H_inlier_ratio: float = 0.8          # COLMAP default, not exposed by the reference's proto
     dyn_num_trials_multiplier: float = 3.0   # RANSACOptions default
+    detect_watermark: bool = True            # TwoViewGeometry::Options defaults, not exposed by the reference's proto
+    watermark_min_inlier_ratio: float = 0.7
+    multiple_ignore_watermark: bool = True
 
 
 @dataclass
@@ -255,7 +266,68 @@ def estimate_uncalibrated(points1: np.ndarray, points2: np.ndarray, matches: np.
     ratio = hr.num_inliers / fr.num_inliers if fr.num_inliers else float("inf")
     tvg.config = PLANAR_OR_PANORAMIC if ratio > opt.max_H_inlier_ratio else UNCALIBRATED
     tvg.inlier_matches = matches[fr.inlier_mask]
+    if opt.detect_watermark and detect_watermark(x1[fr.inlier_mask], x2[fr.inlier_mask], opt, rng):
+        tvg.config = WATERMARK
     return tvg
+
+
+def translation_estimate(x1: np.ndarray, x2: np.ndarray) -> List[np.ndarray]:
+    """TranslationTransformEstimator<2>::Estimate (kMinNumSamples = 1): the mean displacement."""
+    return [(x2 - x1).mean(axis=0)]
+
+
+def translation_sq(t: np.ndarray, x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
+    d = x2 - (x1 + t)
+    return (d * d).sum(axis=1)
+
+
+def detect_watermark(x1_in: np.ndarray, x2_in: np.ndarray, opt: Options, rng: np.random.Generator,
+                     size1=(0.0, 0.0), size2=(0.0, 0.0), border: float = 0.1) -> bool:
+    """TwoViewGeometry::DetectWatermark on the inlier correspondences.  ``size*`` are the cameras' (width, height):
+    the reference passes default-constructed cameras, i.e. (0, 0), which makes the inner box the point (0, 0)."""
+    n = len(x1_in)
+    if n == 0:
+        return False
+
+    def outside(p, size):
+        d = border * float(np.hypot(size[0], size[1]))
+        lo_x, lo_y, hi_x, hi_y = d, d, size[0] - d, size[1] - d
+        inside = (p[:, 0] >= lo_x) & (p[:, 0] <= hi_x) & (p[:, 1] >= lo_y) & (p[:, 1] <= hi_y)
+        return ~inside
+
+    in_border = int((outside(x1_in, size1) & outside(x2_in, size2)).sum())
+    if in_border / n < opt.watermark_min_inlier_ratio:
+        return False
+    from dataclasses import replace
+    wopt = replace(opt, min_inlier_ratio=opt.watermark_min_inlier_ratio)
+    rep = loransac(x1_in, x2_in, translation_estimate, 1, translation_estimate, 1, translation_sq, wopt, rng)
+    return rep.num_inliers / n >= opt.watermark_min_inlier_ratio
+
+
+def estimate_multiple(points1: np.ndarray, points2: np.ndarray, matches: np.ndarray, opt: Options = Options(),
+                      seed: int = 0) -> TwoViewGeometry:
+    """TwoViewGeometry::EstimateMultiple (multiple_models = true, sequential_matching.cc:94-96)."""
+    remaining = np.asarray(matches, dtype=np.uint32).reshape(-1, 2)
+    found: List[TwoViewGeometry] = []
+    k = 0
+    while True:
+        g = estimate_uncalibrated(points1, points2, remaining, opt, seed + 7919 * k)
+        k += 1
+        if g.config == DEGENERATE:
+            break
+        if not (opt.multiple_ignore_watermark and g.config == WATERMARK):
+            found.append(g)
+        inl = {(int(a), int(b)) for a, b in g.inlier_matches}                    # ExtractOutlierMatches
+        remaining = np.asarray([mm for mm in remaining if (int(mm[0]), int(mm[1])) not in inl], dtype=np.uint32).reshape(-1, 2)
+    out = TwoViewGeometry()
+    if not found:
+        out.config = DEGENERATE
+    elif len(found) == 1:
+        out = found[0]
+    else:
+        out.config = MULTIPLE
+        out.inlier_matches = np.concatenate([g.inlier_matches for g in found], axis=0)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- synthetic scenes
@@ -298,3 +370,44 @@ def synthetic_pair(n1: int, n2: int, n_true: int, n_false: int, seed: int, plana
     truth[:n_true] = True
     order = np.argsort(m[:, 0], kind="stable")
     return p1.astype(np.float32), p2.astype(np.float32), m[order], truth[order]
+
+
+def synthetic_shift_pair(n1: int, n2: int, n_true: int, n_false: int, seed: int, shift=(37.0, -12.0), noise_px: float = 0.7,
+                         size=(4000.0, 3000.0)):
+    """Like synthetic_pair, but the correct correspondences are one pure image translation (what a watermark, or a
+    distant scene under a small pan, looks like).  Same return values."""
+    rng = np.random.default_rng(seed)
+    W, Hh = size
+    p1 = rng.uniform([0, 0], [W, Hh], size=(n1, 2))
+    p2 = rng.uniform([0, 0], [W, Hh], size=(n2, 2))
+    i1 = rng.choice(n1, size=n_true + n_false, replace=False)
+    i2 = rng.choice(n2, size=n_true + n_false, replace=False)
+    base = rng.uniform([100, 100], [W - 100, Hh - 100], size=(n_true, 2))
+    p1[i1[:n_true]] = base + noise_px * rng.standard_normal((n_true, 2))
+    p2[i2[:n_true]] = base + np.asarray(shift) + noise_px * rng.standard_normal((n_true, 2))
+    m = np.stack([i1, i2], axis=1).astype(np.uint32)
+    truth = np.zeros(len(m), bool)
+    truth[:n_true] = True
+    order = np.argsort(m[:, 0], kind="stable")
+    return p1.astype(np.float32), p2.astype(np.float32), m[order], truth[order]
+
+
+def synthetic_two_motion_pair(n1: int, n2: int, n_a: int, n_b: int, n_false: int, seed: int):
+    """Two independently moving rigid groups in one image pair (n_a and n_b correct correspondences, each consistent
+    with its own epipolar geometry) plus n_false random matches: the case EstimateMultiple exists for.  Returns
+    (points1, points2, matches, group) with group 0 / 1 for the two motions and -1 for the random matches."""
+    pa1, pa2, ma, ta = synthetic_pair(n1, n2, n_a, 0, seed)
+    pb1, pb2, mb, tb = synthetic_pair(n1, n2, n_b, 0, seed + 1000)
+    rng = np.random.default_rng(seed + 5)
+    p1, p2 = pa1.copy(), pa2.copy()
+    used1, used2 = set(ma[:, 0].tolist()), set(ma[:, 1].tolist())
+    free1 = np.array([i for i in range(n1) if i not in used1])
+    free2 = np.array([i for i in range(n2) if i not in used2])
+    j1 = rng.choice(free1, size=n_b + n_false, replace=False)
+    j2 = rng.choice(free2, size=n_b + n_false, replace=False)
+    p1[j1[:n_b]] = pb1[mb[:, 0]]
+    p2[j2[:n_b]] = pb2[mb[:, 1]]
+    m = np.concatenate([ma, np.stack([j1, j2], axis=1).astype(np.uint32)], axis=0)
+    group = np.concatenate([np.zeros(len(ma), int), np.ones(n_b, int), -np.ones(n_false, int)])
+    order = np.argsort(m[:, 0], kind="stable")
+    return p1, p2, m[order], group[order]

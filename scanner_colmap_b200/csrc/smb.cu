@@ -115,6 +115,15 @@ struct smb_result {
   size_t tvg_cap = 0;
   smb_match* inliers = nullptr;  // pinned [inliers_cap], same offsets as matches
   size_t inliers_cap = 0;
+  // EstimateMultiple rounds (SMB_TVG_MULTIPLE_MODELS): the matches still unexplained, and one round's verdicts
+  smb_match* rem_matches = nullptr;
+  size_t rem_matches_cap = 0;
+  PairOut* rem_po = nullptr;
+  size_t rem_po_cap = 0;
+  smb_tvg* round_tvg = nullptr;
+  size_t round_tvg_cap = 0;
+  smb_match* round_inl = nullptr;
+  size_t round_inl_cap = 0;
   bool verified = false;
   // between smb_match_pairs_begin and smb_result_wait
   bool pending = false;
@@ -508,6 +517,10 @@ void destroy_result(smb_result* r) {
   if (r->counters) cudaFreeHost(r->counters);
   if (r->tvg) cudaFreeHost(r->tvg);
   if (r->inliers) cudaFreeHost(r->inliers);
+  if (r->rem_matches) cudaFreeHost(r->rem_matches);
+  if (r->rem_po) cudaFreeHost(r->rem_po);
+  if (r->round_tvg) cudaFreeHost(r->round_tvg);
+  if (r->round_inl) cudaFreeHost(r->round_inl);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   delete r;
 }
@@ -1364,7 +1377,7 @@ int smb_get_timing(const smb_handle* h, smb_timing* t) {
 
 void smb_default_tvg_options(smb_tvg_options* o) {
   if (!o) return;
-  std::memset(o, 0, sizeof *o);
+  std::memset(o, 0, sizeof *o);  // flags = 0: watermark detection on, one model
   o->min_num_inliers = 15;     // colmap.proto:41
   o->min_num_trials = 30;      // colmap.proto:32
   o->max_num_trials = 10000;   // colmap.proto:33
@@ -1410,8 +1423,9 @@ int smb_result_verify(smb_handle* h, smb_result* r, const smb_tvg_options* opts)
   }
   SMB_CUDA(h, cudaSetDevice(h->device));
   static_assert(sizeof(smb_tvg) == sizeof(tvg::Out), "smb_tvg mirrors tvg::Out");
-  if (!reserve_pinned(&r->tvg, &r->tvg_cap, r->npairs) || !reserve_pinned(&r->inliers, &r->inliers_cap, std::max<size_t>(r->total, 1)) ||
-      cudaSuccess != h->d_pts.reserve(std::max<size_t>(r->total, 1))) {
+  const size_t total = std::max<size_t>(r->total, 1);
+  if (!reserve_pinned(&r->tvg, &r->tvg_cap, r->npairs) || !reserve_pinned(&r->inliers, &r->inliers_cap, total) ||
+      cudaSuccess != h->d_pts.reserve(2 * total)) {  // correspondences of all matches + of the inliers
     cudaGetLastError();
     return fail(h, SMB_ENOMEM, "verification buffers (%zu pairs, %zu matches)", r->npairs, r->total);
   }
@@ -1423,12 +1437,94 @@ int smb_result_verify(smb_handle* h, smb_result* r, const smb_tvg_options* opts)
   to.confidence = o.confidence;
   to.min_inlier_ratio = o.min_inlier_ratio;
   to.max_H_inlier_ratio = o.max_h_inlier_ratio;
+  to.watermark_min_inlier_ratio = 0.7;  // TwoViewGeometry::Options default, not exposed by the reference's proto
+  to.detect_watermark = (o.flags & SMB_TVG_NO_WATERMARK) ? 0 : 1;
+  to.pad_ = 0;
   to.seed = o.seed;
-  tvg::verify_kernel<<<(unsigned)r->npairs, tvg::kThreads, 0, h->stream>>>(
-      h->d_pairs.p, reinterpret_cast<const uint2*>(r->matches), r->pair_out, h->kp_pool, h->d_pts.p, to,
-      reinterpret_cast<tvg::Out*>(r->tvg), reinterpret_cast<uint2*>(r->inliers));
-  SMB_CUDA(h, cudaGetLastError());
-  SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!(o.flags & SMB_TVG_MULTIPLE_MODELS)) {
+    tvg::verify_kernel<<<(unsigned)r->npairs, tvg::kThreads, 0, h->stream>>>(
+        h->d_pairs.p, reinterpret_cast<const uint2*>(r->matches), r->pair_out, h->kp_pool, h->d_pts.p, h->d_pts.p + total, to,
+        reinterpret_cast<tvg::Out*>(r->tvg), reinterpret_cast<uint2*>(r->inliers));
+    SMB_CUDA(h, cudaGetLastError());
+    SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    r->verified = true;
+    return SMB_OK;
+  }
+  // ---- TwoViewGeometry::EstimateMultiple: rounds of the same kernel over the matches no accepted model has explained yet.
+  // The bookkeeping between rounds (a few thousand matches per pair) runs on the host; a round costs one launch + one sync.
+  if (!reserve_pinned(&r->rem_matches, &r->rem_matches_cap, total) || !reserve_pinned(&r->rem_po, &r->rem_po_cap, r->npairs) ||
+      !reserve_pinned(&r->round_tvg, &r->round_tvg_cap, r->npairs) || !reserve_pinned(&r->round_inl, &r->round_inl_cap, total))
+    return fail(h, SMB_ENOMEM, "verification buffers (%zu pairs, %zu matches)", r->npairs, r->total);
+  std::memcpy(r->rem_matches, r->matches, r->total * sizeof(smb_match));
+  std::memcpy(r->rem_po, r->pair_out, r->npairs * sizeof(PairOut));
+  std::vector<uint8_t> done(r->npairs, 0);
+  std::vector<uint32_t> models(r->npairs, 0), appended(r->npairs, 0);
+  std::vector<int32_t> trials_f(r->npairs, 0), trials_h(r->npairs, 0);
+  for (size_t i = 0; i < r->npairs; ++i) {
+    smb_tvg& t = r->tvg[i];
+    std::memset(&t, 0, sizeof t);
+    t.config = tvg::kDegenerate;
+    t.inlier_start = r->pair_out[i].start;
+  }
+  for (uint32_t round = 0;; ++round) {
+    to.seed = o.seed + 7919ull * round;
+    tvg::verify_kernel<<<(unsigned)r->npairs, tvg::kThreads, 0, h->stream>>>(
+        h->d_pairs.p, reinterpret_cast<const uint2*>(r->rem_matches), r->rem_po, h->kp_pool, h->d_pts.p, h->d_pts.p + total, to,
+        reinterpret_cast<tvg::Out*>(r->round_tvg), reinterpret_cast<uint2*>(r->round_inl));
+    SMB_CUDA(h, cudaGetLastError());
+    SMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    bool any_active = false;
+    for (size_t i = 0; i < r->npairs; ++i) {
+      if (done[i]) continue;
+      const smb_tvg& rt = r->round_tvg[i];
+      trials_f[i] += rt.trials_f;
+      trials_h[i] += rt.trials_h;
+      if (rt.config == tvg::kDegenerate) {
+        done[i] = 1;
+        r->rem_po[i].count = 0;  // later rounds return at once for this pair
+        continue;
+      }
+      const smb_match* inl = r->round_inl + rt.inlier_start;
+      const uint32_t n_inl = rt.inlier_count;
+      if (rt.config != tvg::kWatermark) {  // multiple_ignore_watermark = true: a watermark's inliers are removed, not kept
+        if (models[i] == 0) {
+          r->tvg[i] = rt;  // a single accepted model is reported as it is
+          r->tvg[i].inlier_start = r->pair_out[i].start;
+        }
+        std::memcpy(r->inliers + r->pair_out[i].start + appended[i], inl, n_inl * sizeof(smb_match));
+        appended[i] += n_inl;
+        ++models[i];
+      }
+      // ExtractOutlierMatches: the round's inliers are an ordered subsequence of the remaining matches
+      smb_match* rem = r->rem_matches + r->rem_po[i].start;
+      uint32_t keep = 0, q = 0;
+      for (uint32_t x = 0; x < r->rem_po[i].count; ++x) {
+        if (q < n_inl && rem[x].idx1 == inl[q].idx1 && rem[x].idx2 == inl[q].idx2) ++q;
+        else rem[keep++] = rem[x];
+      }
+      r->rem_po[i].count = keep;
+      if (n_inl == 0 || (int32_t)keep < o.min_num_inliers) {  // the next Estimate would be DEGENERATE
+        done[i] = 1;
+        r->rem_po[i].count = 0;
+      } else {
+        any_active = true;
+      }
+    }
+    if (!any_active) break;
+  }
+  for (size_t i = 0; i < r->npairs; ++i) {
+    smb_tvg& t = r->tvg[i];
+    t.inlier_count = appended[i];
+    t.trials_f = trials_f[i];
+    t.trials_h = trials_h[i];
+    if (models[i] > 1) {  // COLMAP: config = MULTIPLE, inlier_matches = all models' inliers, everything else default
+      t.config = tvg::kMultiple;
+      t.num_inliers_f = (int32_t)appended[i];
+      t.num_inliers_h = 0;
+      std::memset(t.F, 0, sizeof t.F);
+      std::memset(t.H, 0, sizeof t.H);
+    }
+  }
   r->verified = true;
   return SMB_OK;
 }

@@ -27,7 +27,8 @@ namespace smb {
 namespace tvg {
 
 constexpr int kThreads = 128;
-enum Config : int32_t { kUndefined = 0, kDegenerate = 1, kCalibrated = 2, kUncalibrated = 3, kPlanarOrPanoramic = 6 };
+enum Config : int32_t { kUndefined = 0, kDegenerate = 1, kCalibrated = 2, kUncalibrated = 3, kPlanarOrPanoramic = 6, kWatermark = 7,
+                        kMultiple = 8 };
 
 struct Options {
   int32_t min_num_inliers;
@@ -37,6 +38,9 @@ struct Options {
   double confidence;
   double min_inlier_ratio;
   double max_H_inlier_ratio;
+  double watermark_min_inlier_ratio;  // TwoViewGeometry::Options default 0.7
+  int32_t detect_watermark;           // TwoViewGeometry::Options default true
+  int32_t pad_;
   unsigned long long seed;
 };
 
@@ -537,19 +541,100 @@ __device__ int loransac(Shared& sh, const float4* __restrict__ pts, uint32_t m, 
   return trials;
 }
 
+// TwoViewGeometry::DetectWatermark on the n inlier correspondences q[0, n) of the accepted geometry, with the
+// reference's default-constructed cameras (width = height = 0, sequential_matching.cc:89): the "inner" box is the point
+// (0, 0), so every inlier not exactly there counts as lying in the border region, and what decides is whether at least
+// watermark_min_inlier_ratio of the inliers fit ONE pure image translation within max_error.  COLMAP runs a LORANSAC
+// over one-point samples for that (at most ComputeNumTrials(0.7, k = 1) = 18 trials); here every thread tries one
+// random inlier's displacement (128 samples), the best goes through the local optimisation (mean displacement of its
+// inliers), as in loransac() above.  Whole CTA; the verdict is uniform.
+__device__ bool watermark_test(Shared& sh, const float4* __restrict__ q, uint32_t n, const Options& o, unsigned long long seed) {
+  const int tid = threadIdx.x;
+  const double thr = o.max_error * o.max_error;
+  if (n == 0) return false;
+  if (tid == 0) { sh.count = 0; sh.best_cnt = 0; sh.best_sum = 1e300; }
+  __syncthreads();
+  int nb = 0;
+  for (uint32_t i = tid; i < n; i += kThreads) {
+    const float4 p = q[i];
+    if (!(p.x == 0.f && p.y == 0.f) && !(p.z == 0.f && p.w == 0.f)) ++nb;
+  }
+  atomicAdd(&sh.count, nb);
+  __syncthreads();
+  if ((double)sh.count / (double)n < o.watermark_min_inlier_ratio) return false;
+  // ---- one-point samples
+  unsigned long long rs = seed ^ (0xA0761D6478BD642Full * (unsigned long long)(tid + 1));
+  const float4 s = q[(uint32_t)(rng_next(rs) % (unsigned long long)n)];
+  const double tx = (double)s.z - (double)s.x, ty = (double)s.w - (double)s.y;
+  int cnt = 0;
+  double sum = 0.0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const float4 p = q[i];
+    const double dx = (double)p.z - (double)p.x - tx, dy = (double)p.w - (double)p.y - ty, r = dx * dx + dy * dy;
+    if (r <= thr) { ++cnt; sum += r; }
+  }
+  sh.t_cnt[tid] = cnt;
+  sh.t_sum[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int bt = 0;
+    for (int t = 1; t < kThreads; ++t)
+      if (sh.t_cnt[t] > sh.t_cnt[bt] || (sh.t_cnt[t] == sh.t_cnt[bt] && sh.t_sum[t] < sh.t_sum[bt])) bt = t;
+    sh.cand_thread = bt;
+    sh.best_cnt = sh.t_cnt[bt];
+    sh.best_sum = sh.t_sum[bt];
+  }
+  __syncthreads();
+  if (tid == sh.cand_thread) { sh.model[0] = tx; sh.model[1] = ty; }
+  if (tid < 2) sh.sums[tid] = 0.0;
+  __syncthreads();
+  if (sh.best_cnt > 1) {  // local optimisation: the mean displacement of the best sample's inliers, adopted if it is better
+    const double bx = sh.model[0], by = sh.model[1];
+    double ax = 0.0, ay = 0.0;
+    for (uint32_t i = tid; i < n; i += kThreads) {
+      const float4 p = q[i];
+      const double ux = (double)p.z - (double)p.x, uy = (double)p.w - (double)p.y;
+      if ((ux - bx) * (ux - bx) + (uy - by) * (uy - by) <= thr) { ax += ux; ay += uy; }
+    }
+    atomicAdd(&sh.sums[0], ax);
+    atomicAdd(&sh.sums[1], ay);
+    if (tid == 0) { sh.cand_cnt = 0; sh.cand_sum = 0.0; }
+    __syncthreads();
+    const double mx = sh.sums[0] / (double)sh.best_cnt, my = sh.sums[1] / (double)sh.best_cnt;
+    int c2 = 0;
+    double s2 = 0.0;
+    for (uint32_t i = tid; i < n; i += kThreads) {
+      const float4 p = q[i];
+      const double dx = (double)p.z - (double)p.x - mx, dy = (double)p.w - (double)p.y - my, r = dx * dx + dy * dy;
+      if (r <= thr) { ++c2; s2 += r; }
+    }
+    atomicAdd(&sh.cand_cnt, c2);
+    atomicAdd(&sh.cand_sum, s2);
+    __syncthreads();
+    if (tid == 0 && (sh.cand_cnt > sh.best_cnt || (sh.cand_cnt == sh.best_cnt && sh.cand_sum < sh.best_sum))) {
+      sh.best_cnt = sh.cand_cnt;
+      sh.best_sum = sh.cand_sum;
+    }
+    __syncthreads();
+  }
+  return (double)sh.best_cnt / (double)n >= o.watermark_min_inlier_ratio;
+}
+
 // grid = pairs; block = kThreads.  `matches` / `pair_out` are the matcher's result (pinned host memory, read through
 // UVA), `xy` holds one float2 per descriptor-pool row, `pts` is device scratch of one float4 per match, `inliers` the
 // pinned output buffer (same offsets as `matches`).
 __global__ void __launch_bounds__(kThreads)
 verify_kernel(const PairMeta* __restrict__ pairs, const uint2* __restrict__ matches, const PairOut* __restrict__ pair_out,
-              const float2* __restrict__ xy, float4* __restrict__ pts_all, Options o, Out* __restrict__ out,
-              uint2* __restrict__ inliers) {
+              const float2* __restrict__ xy, float4* __restrict__ pts_all, float4* __restrict__ ipts_all, Options o,
+              Out* __restrict__ out, uint2* __restrict__ inliers) {
+  // ipts_all: device scratch like pts_all; receives the inlier correspondences (for the watermark test)
   __shared__ Shared sh;
   const PairMeta pm = pairs[blockIdx.x];
   const PairOut po = pair_out[pm.out_slot];
   const uint32_t m = po.count;
   const uint2* mt = matches + po.start;
   float4* pts = pts_all + po.start;
+  float4* ipts = ipts_all + po.start;
   const int tid = threadIdx.x;
   Out* res = out + pm.out_slot;
   for (uint32_t i = tid; i < m; i += kThreads) {
@@ -598,9 +683,17 @@ verify_kernel(const PairMeta* __restrict__ pairs, const uint2* __restrict__ matc
       if (w < (int)wid) before += sh.warp_sums[w];
       total += sh.warp_sums[w];
     }
-    if (in) inliers[po.start + running + before + __popc(ballot & ((1u << lane) - 1))] = mt[i];
+    if (in) {
+      const uint32_t pos = running + before + __popc(ballot & ((1u << lane) - 1));
+      inliers[po.start + pos] = mt[i];
+      ipts[pos] = pts[i];
+    }
     running += total;
   }
+  if (tid < 9) res->F[tid] = sh.model[tid];  // before the watermark test reuses sh.model
+  __syncthreads();
+  if (config != kDegenerate && o.detect_watermark && watermark_test(sh, ipts, running, o, seed ^ 0x2545F4914F6CDD1Dull))
+    config = kWatermark;
   if (tid == 0) {
     res->config = config;
     res->num_inliers_F = inl_f;
@@ -609,7 +702,6 @@ verify_kernel(const PairMeta* __restrict__ pairs, const uint2* __restrict__ matc
     res->trials_H = trials_h;
     res->inlier_start = po.start;
     res->inlier_count = running;
-    for (int k = 0; k < 9; ++k) res->F[k] = sh.model[k];
   }
 }
 

@@ -46,9 +46,12 @@ class smb_timing(ctypes.Structure):
                 ("pad_", ctypes.c_float)]
 
 
+SMB_TVG_NO_WATERMARK, SMB_TVG_MULTIPLE_MODELS = 1, 2   # include/smb.h
+
+
 class smb_tvg_options(ctypes.Structure):
     _fields_ = [("min_num_inliers", ctypes.c_int32), ("min_num_trials", ctypes.c_int32), ("max_num_trials", ctypes.c_int32),
-                ("pad_", ctypes.c_int32), ("max_error", ctypes.c_double), ("confidence", ctypes.c_double),
+                ("flags", ctypes.c_int32), ("max_error", ctypes.c_double), ("confidence", ctypes.c_double),
                 ("min_inlier_ratio", ctypes.c_double), ("max_h_inlier_ratio", ctypes.c_double), ("seed", ctypes.c_uint64)]
 
 
@@ -367,13 +370,16 @@ class MatchResult:
         a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(cnt.value, 2))
         return a.copy()
 
-    def verify(self, **opts) -> None:
+    def verify(self, detect_watermark: bool = True, multiple_models: bool = False, **opts) -> None:
         """Two-view geometry verification of every pair on the GPU (TwoViewGeometry::Estimate with the reference's
-        dummy cameras: uncalibrated F / H LORANSAC).  Options: min_num_inliers, min_num_trials, max_num_trials,
-        max_error, confidence, min_inlier_ratio, max_h_inlier_ratio, seed (defaults: colmap.proto:24-44)."""
+        dummy cameras: uncalibrated F / H LORANSAC, then the watermark test).  Options: min_num_inliers, min_num_trials,
+        max_num_trials, max_error, confidence, min_inlier_ratio, max_h_inlier_ratio, seed (defaults:
+        colmap.proto:24-44); ``detect_watermark`` (COLMAP default true), ``multiple_models`` (colmap.proto:45:
+        TwoViewGeometry::EstimateMultiple)."""
         self.wait()
         o = smb_tvg_options()
         self._m._L.smb_default_tvg_options(ctypes.byref(o))
+        o.flags = (0 if detect_watermark else SMB_TVG_NO_WATERMARK) | (SMB_TVG_MULTIPLE_MODELS if multiple_models else 0)
         for k, v in opts.items():
             if not hasattr(o, k):
                 raise TypeError(f"unknown option {k}")

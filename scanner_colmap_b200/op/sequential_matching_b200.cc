@@ -238,6 +238,7 @@ class SequentialMatchingB200Kernel : public scanner::StenciledBatchedKernel, pub
     tvg_opts_.min_num_trials = args_.siftargs.min_num_trials;
     tvg_opts_.max_num_trials = args_.siftargs.max_num_trials;
     tvg_opts_.min_inlier_ratio = args_.siftargs.min_inlier_ratio;
+    tvg_opts_.flags = args_.siftargs.multiple_models ? SMB_TVG_MULTIPLE_MODELS : 0;  // sequential_matching.cc:94-96
     gpu_ = acquire_gpu(device, opts_);
   }
   ~SequentialMatchingB200Kernel() override { release_gpu(gpu_); }

@@ -97,3 +97,80 @@ def test_too_few_matches_are_degenerate_and_options_are_honoured(tv):
             mt.put_image(1, d2)                                     # descriptors replaced: the keypoints are gone
             with pytest.raises(Exception):
                 r2.verify()
+
+
+def _planted(tv, p1, p2, m, seed):
+    """Descriptors for which the matcher returns the planted match list ``m`` (see _scene)."""
+    d1 = synth.make_image(9000 + 2 * seed, len(p1), shared_frac=0.0)
+    d2 = synth.make_image(9001 + 2 * seed, len(p2), shared_frac=0.0)
+    d2[m[:, 1]] = d1[m[:, 0]]
+    return d1, d2
+
+
+def _surviving(got_matches, m, *labels):
+    """The planted rows the matcher returned (a few fail the distance test), with their labels."""
+    got = set(map(tuple, got_matches.tolist()))
+    keep = np.array([tuple(x) in got for x in m.tolist()])
+    assert got <= set(map(tuple, m.tolist())) and keep.sum() >= 0.98 * len(m)
+    return (m[keep],) + tuple(l[keep] for l in labels)
+
+
+def test_watermark_configuration(tv):
+    # TwoViewGeometry::DetectWatermark with the reference's dummy cameras: inliers that are one image translation
+    p1, p2, m, truth = tv.synthetic_shift_pair(2048, 2048, 600, 200, seed=31)
+    q1, q2, m2, truth2 = tv.synthetic_pair(2048, 2048, 600, 200, seed=32)
+    d1, d2 = _planted(tv, p1, p2, m, 31)
+    e1, e2 = _planted(tv, q1, q2, m2, 32)
+    with SiftMatcher() as mt:
+        mt.put_images([0, 1, 2, 3], [d1, d2, e1, e2])
+        for i, p in enumerate((p1, p2, q1, q2)):
+            mt.put_keypoints(i, p)
+        with mt.match_pairs_result(np.array([[0, 1], [2, 3]], dtype=np.uint32)) as r:
+            r.verify(seed=3)
+            m, truth = _surviving(r.matches(0), m, truth)
+            want = tv.estimate_uncalibrated(p1, p2, m, seed=1)
+            g, inl = r.tvg(0), r.inliers(0)
+            assert g["config"] == want.config == tv.WATERMARK
+            assert _iou(inl, want.inlier_matches) >= 0.95                    # the inlier matches are still those of F
+            assert len(set(map(tuple, inl.tolist())) & set(map(tuple, m[truth].tolist()))) >= 0.97 * truth.sum()
+            assert r.tvg(1)["config"] == tv.UNCALIBRATED                     # a general scene is not a translation
+            r.verify(seed=3, detect_watermark=False)
+            assert r.tvg(0)["config"] == tv.PLANAR_OR_PANORAMIC and r.tvg(1)["config"] == tv.UNCALIBRATED
+
+
+def test_multiple_models(tv):
+    # TwoViewGeometry::EstimateMultiple (siftMatchingArgs.multiple_models, sequential_matching.cc:94-96)
+    p1, p2, m, group = tv.synthetic_two_motion_pair(2048, 2048, 400, 250, 120, seed=41)
+    q1, q2, m2, truth2 = tv.synthetic_pair(2048, 2048, 500, 150, seed=42)
+    w1, w2, mw, truthw = tv.synthetic_shift_pair(2048, 2048, 300, 80, seed=43)
+    ds = [_planted(tv, a, b, mm, s) for a, b, mm, s in ((p1, p2, m, 41), (q1, q2, m2, 42), (w1, w2, mw, 43))]
+    with SiftMatcher() as mt:
+        mt.put_images(list(range(6)), [d for pair in ds for d in pair])
+        for i, p in enumerate((p1, p2, q1, q2, w1, w2)):
+            mt.put_keypoints(i, np.asarray(p, dtype=np.float32))
+        with mt.match_pairs_result(np.array([[0, 1], [2, 3], [4, 5]], dtype=np.uint32)) as r:
+            r.verify(seed=2, multiple_models=True)
+            # two independently moving groups: MULTIPLE, the inlier matches of both models, F / H left at zero
+            m, group = _surviving(r.matches(0), m, group)
+            want = tv.estimate_multiple(p1, p2, m, seed=1)
+            g, inl = r.tvg(0), r.inliers(0)
+            assert g["config"] == want.config == tv.MULTIPLE and not g["F"].any() and not g["H"].any()
+            got = set(map(tuple, inl.tolist()))
+            assert len(got) == len(inl)                                      # no match is reported twice
+            for k in (0, 1):
+                grp = set(map(tuple, m[group == k].tolist()))
+                assert len(got & grp) >= 0.97 * len(grp)
+            assert len(got & set(map(tuple, m[group == -1].tolist()))) <= 8
+            assert _iou(inl, want.inlier_matches) >= 0.95
+            # one motion: the single geometry as it is (same contract as Estimate)
+            m2, truth2 = _surviving(r.matches(1), m2, truth2)
+            g1, inl1 = r.tvg(1), r.inliers(1)
+            assert g1["config"] == tv.UNCALIBRATED and g1["F"].any()
+            assert _iou(inl1, tv.estimate_multiple(q1, q2, m2, seed=1).inlier_matches) >= 0.95
+            assert np.all(np.diff(inl1[:, 0].astype(np.int64)) > 0)
+            # a watermark is skipped and nothing else is left: DEGENERATE, no inlier matches
+            assert r.tvg(2)["config"] == tv.DEGENERATE and len(r.inliers(2)) == 0
+            # the same result object verified again without the option: Estimate's answers
+            r.verify(seed=2)
+            assert r.tvg(0)["config"] == tv.UNCALIBRATED and len(r.inliers(0)) < 0.7 * len(got)
+            assert r.tvg(2)["config"] == tv.WATERMARK and len(r.inliers(2)) >= 290

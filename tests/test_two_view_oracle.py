@@ -92,3 +92,53 @@ def test_estimate_uncalibrated_decisions(tv):
     g2 = tv.estimate_uncalibrated(p1, p2, m, seed=4)
     inl2 = set(map(tuple, g2.inlier_matches.tolist()))
     assert len(inl & inl2) / len(inl | inl2) >= 0.95
+
+
+def test_watermark_detection_with_the_references_dummy_cameras(tv):
+    # TwoViewGeometry::DetectWatermark: the inliers are one pure image translation.  With default-constructed cameras
+    # (width = height = 0, sequential_matching.cc:89) the border-region condition holds for every inlier.
+    p1, p2, m, truth = tv.synthetic_shift_pair(3000, 3000, 500, 150, seed=3)
+    g = tv.estimate_uncalibrated(p1, p2, m, seed=1)
+    assert g.config == tv.WATERMARK and 495 <= len(g.inlier_matches) <= 515   # the inlier matches are still reported
+    assert tv.estimate_uncalibrated(p1, p2, m, tv.Options(detect_watermark=False), seed=1).config == tv.PLANAR_OR_PANORAMIC
+    # a general scene is not a translation, whatever the seed
+    q1, q2, m2, _ = tv.synthetic_pair(3000, 3000, 400, 120, seed=8)
+    assert all(tv.estimate_uncalibrated(q1, q2, m2, seed=s).config == tv.UNCALIBRATED for s in range(3))
+    # the test itself: 75 % of the correspondences on one translation passes, 60 % does not; real cameras change the
+    # border condition (points in the image centre do not count)
+    rng = np.random.default_rng(0)
+    x1 = rng.uniform(200, 2800, size=(200, 2))
+    x2 = x1 + np.array([25.0, -40.0])
+    x2[150:] += rng.uniform(30, 300, size=(50, 2))
+    assert tv.detect_watermark(x1, x2, tv.Options(), np.random.default_rng(1))
+    x2[120:150] += rng.uniform(30, 300, size=(30, 2))
+    assert not tv.detect_watermark(x1, x2, tv.Options(), np.random.default_rng(1))
+    x2 = x1 + np.array([25.0, -40.0])
+    assert not tv.detect_watermark(x1, x2, tv.Options(), np.random.default_rng(1), size1=(3000, 3000), size2=(3000, 3000))
+    assert tv.translation_sq(np.array([25.0, -40.0]), x1, x2).max() < 1e-18
+    (t,) = tv.translation_estimate(x1, x2)
+    assert np.allclose(t, [25.0, -40.0])
+
+
+def test_estimate_multiple(tv):
+    # TwoViewGeometry::EstimateMultiple (multiple_models, sequential_matching.cc:94-96)
+    p1, p2, m, group = tv.synthetic_two_motion_pair(3000, 3000, 400, 250, 120, seed=7)
+    g = tv.estimate_multiple(p1, p2, m, seed=1)
+    assert g.config == tv.MULTIPLE and not g.F.any() and not g.H.any()
+    inl = set(map(tuple, g.inlier_matches.tolist()))
+    for k in (0, 1):
+        grp = set(map(tuple, m[group == k].tolist()))
+        assert len(inl & grp) >= 0.97 * len(grp)
+    assert len(inl & set(map(tuple, m[group == -1].tolist()))) <= 6
+    single = tv.estimate_uncalibrated(p1, p2, m, seed=1)                      # one model explains one motion only
+    assert single.config == tv.UNCALIBRATED and len(single.inlier_matches) < 0.7 * len(inl)
+    # one motion: the single geometry is returned as it is
+    q1, q2, m2, truth = tv.synthetic_pair(3000, 3000, 400, 120, seed=8)
+    one = tv.estimate_multiple(q1, q2, m2, seed=3)
+    assert one.config == tv.UNCALIBRATED and one.F.any() and 395 <= len(one.inlier_matches) <= 410
+    # a watermark is skipped (multiple_ignore_watermark): nothing else left -> DEGENERATE, no inlier matches
+    w1, w2, mw, _ = tv.synthetic_shift_pair(3000, 3000, 300, 60, seed=5)
+    none = tv.estimate_multiple(w1, w2, mw, seed=1)
+    assert none.config == tv.DEGENERATE and len(none.inlier_matches) == 0
+    kept = tv.estimate_multiple(w1, w2, mw, tv.Options(multiple_ignore_watermark=False), seed=1)
+    assert kept.config == tv.WATERMARK and len(kept.inlier_matches) >= 295
