@@ -41,6 +41,32 @@ def test_default_options_match_colmap_proto(built):
     assert o.engine == matcher.ENGINE_TCGEN05
 
 
+def test_tvg_options_mirror_and_defaults(built):
+    """The ctypes mirror of smb_tvg_options has the C layout (checked by compiling a two-line probe against the header),
+    its flag constants are the header's, and the defaults are colmap.proto's (24-44) with COLMAP's watermark test on."""
+    import shutil
+    import tempfile
+    L = matcher.load_library()
+    o = matcher.smb_tvg_options()
+    L.smb_default_tvg_options(ctypes.byref(o))
+    assert (o.min_num_inliers, o.min_num_trials, o.max_num_trials, o.flags) == (15, 30, 10000, 0)
+    assert (o.max_error, o.confidence, o.min_inlier_ratio, o.max_h_inlier_ratio) == (4.0, 0.999, 0.25, 0.8)
+    hdr = open(os.path.join(ROOT, "include", "smb.h")).read()
+    for name, val in (("SMB_TVG_NO_WATERMARK", matcher.SMB_TVG_NO_WATERMARK), ("SMB_TVG_MULTIPLE_MODELS", matcher.SMB_TVG_MULTIPLE_MODELS)):
+        assert re.search(rf"#define {name} {val}\b", hdr), name
+    if shutil.which("gcc"):
+        with tempfile.TemporaryDirectory() as d:
+            src = os.path.join(d, "probe.c")
+            open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "smb.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                                 'sizeof(smb_tvg_options), offsetof(smb_tvg_options, flags), offsetof(smb_tvg_options, max_error), '
+                                 'offsetof(smb_tvg_options, seed), sizeof(smb_tvg), offsetof(smb_tvg, F)); return 0; }\n')
+            exe = os.path.join(d, "probe")
+            subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+            got = [int(x) for x in subprocess.check_output([exe]).split()]
+        t, g = matcher.smb_tvg_options, matcher.smb_tvg
+        assert got == [ctypes.sizeof(t), t.flags.offset, t.max_error.offset, t.seed.offset, ctypes.sizeof(g), g.F.offset]
+
+
 def test_sass_is_blackwell_native(built):
     """The shipped cubin must contain the tcgen05 / TMA / TMEM instructions, for sm_100a only."""
     out = subprocess.run(["cuobjdump", "-sass", matcher.LIB_PATH], capture_output=True, text=True)
