@@ -91,3 +91,33 @@ def test_kernel_args_defaults_and_overrides(H):
                                   min_num_inliers=3, overlap=20, max_error=2.5)
     assert parse(a) == (1, (0.9, 1.1, 0, 100, 3, 20, 2.5))
     assert parse(b"\x22\x7f")[0] == 0   # truncated embedded message is reported, defaults kept
+
+
+def test_two_view_geometry_rows_roundtrip_property(H):
+    """Random TwoViewGeometry lists (every configuration value incl. WATERMARK = 7 and MULTIPLE = 8, empty and long
+    inlier lists) survive Python writer -> C++ reader -> C++ writer -> Python reader byte for byte (io.cc:224-297)."""
+    from hypothesis import given, settings, strategies as st
+
+    tvg = st.builds(
+        lambda cfg, vals, m, seed: wire.TwoViewGeometry(
+            config=cfg, E=vals[0:9], F=vals[9:18], H=vals[18:27], qvec=vals[27:31], tvec=vals[31:34], tri_angle=vals[34],
+            inlier_matches=np.random.default_rng(seed).integers(0, 2 ** 32, size=(m, 2), dtype=np.uint64).astype(np.uint32)),
+        st.integers(0, 8), st.lists(st.floats(-1e6, 1e6, allow_nan=False), min_size=35, max_size=35), st.integers(0, 300),
+        st.integers(0, 2 ** 31))
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(tvg, min_size=0, max_size=5))
+    def check(tvgs):
+        b = wire.encode_two_view_geometries(tvgs)
+        assert len(b) == 12 + sum(284 + 8 + 8 * len(t.inlier_matches) for t in tvgs)
+        out = ctypes.create_string_buffer(max(len(b), 1))
+        assert H.smb_wire_tvg_roundtrip(b, len(b), out, len(b)) == len(b) and out.raw[:len(b)] == b
+        back = wire.decode_two_view_geometries(b)
+        assert len(back) == len(tvgs)
+        for x, y in zip(tvgs, back):
+            assert x.config == y.config and np.array_equal(x.inlier_matches, y.inlier_matches)
+            assert np.array_equal(np.asarray(x.F, float).ravel(), np.asarray(y.F, float).ravel())
+        if len(b) > 12:
+            assert H.smb_wire_tvg_roundtrip(b[:-3], len(b) - 3, out, len(b)) == 0     # truncated rows are refused
+
+    check()
