@@ -118,3 +118,34 @@ def test_halo_exchange_world2_gloo():
     assert res[0][2] == overlap - 1 and res[0][3] == 0          # rank 0 receives its halo, sends nothing
     assert res[1][2] == 0 and res[1][3] == overlap - 1
     assert res[0][4] + res[1][4] == (overlap - 1) * n - overlap * (overlap - 1) // 2
+
+
+def test_plans_property_random_sizes():
+    """Random ragged image sets, overlaps and world sizes: both plans cover every pair exactly once, the send / recv
+    lists of all ranks agree, and every row a rank's pairs name is owned or received."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 16384), min_size=1, max_size=40), st.integers(2, 45), st.integers(1, 8))
+    def check(sizes, overlap, world):
+        n = len(sizes)
+        want = {tuple(p) for p in sequential_pairs(list(range(n)), overlap).tolist()}
+        plans = [sharding.plan(sizes, overlap, world, r) for r in range(world)]
+        seen = [tuple(x) for p in plans for x in p.pairs.tolist()]
+        assert len(seen) == len(set(seen)) and set(seen) == want
+        assert {(row, r, dst) for r, p in enumerate(plans) for row, dst in p.send} == \
+               {(row, src, r) for r, p in enumerate(plans) for row, src in p.recv}
+        for p in plans:
+            s, e = p.own
+            assert {int(x) for x in p.pairs.reshape(-1)} <= set(range(s, e)) | {row for row, _ in p.recv}
+        ex = [sharding.plan_exhaustive(sizes, world, r) for r in range(world)]
+        seen = [tuple(x) for p in ex for x in p.pairs.tolist()]
+        assert len(seen) == len(set(seen)) == n * (n - 1) // 2
+        assert {(row, r, dst) for r, p in enumerate(ex) for row, dst in p.send} == \
+               {(row, src, r) for r, p in enumerate(ex) for row, src in p.recv}
+        owned = [set(range(*p.own)) for p in ex]
+        assert sorted(x for o in owned for x in o) == list(range(n))
+        for r, p in enumerate(ex):
+            assert {int(x) for x in p.pairs.reshape(-1)} <= owned[r] | {row for row, _ in p.recv}
+
+    check()
