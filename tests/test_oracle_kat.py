@@ -130,3 +130,34 @@ def test_committed_golden_fixture(oracle):
         got = oracle.match(a, b, max_ratio=case["max_ratio"], max_distance=case["max_distance"],
                            cross_check=case["cross_check"])
         assert got.tolist() == case["matches"], case
+
+
+def test_c_oracle_and_numpy_mirror_agree_property(oracle):
+    """The two independent restatements (C, numpy) agree on random shapes, options and descriptor distributions that
+    stress the decision boundaries: duplicated rows (ties), scaled-up rows (saturation above 512^2), sparse rows."""
+    from hypothesis import given, settings, strategies as st
+    from scanner_colmap_b200 import synth
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 90), st.integers(0, 90), st.booleans(), st.sampled_from([0.0, 0.6, 0.8, 0.95, 1.0, 1.5]),
+           st.sampled_from([0.0, 0.3, 0.7, 1.0, 1.5707964, 3.0]), st.integers(0, 2 ** 20), st.sampled_from(["sift", "dup", "hot", "sparse"]))
+    def check(n1, n2, cc, ratio, dist, seed, kind):
+        rng = np.random.default_rng(seed)
+        a = synth.make_image(seed, n1, track_step=4) if n1 else np.empty((0, 128), np.uint8)
+        b = synth.make_image(seed + 1, n2, track_step=4) if n2 else np.empty((0, 128), np.uint8)
+        if kind == "dup" and n1 > 1 and n2 > 1:
+            b[rng.integers(0, n2, n2 // 2)] = b[0]
+            a[rng.integers(0, n1, n1 // 2)] = b[0]
+        elif kind == "hot" and n1 and n2:
+            a = np.minimum(a.astype(np.int32) * 3, 255).astype(np.uint8)
+            b = np.minimum(b.astype(np.int32) * 3, 255).astype(np.uint8)
+        elif kind == "sparse":
+            a[:, 16:] = 0
+            b[:, 16:] = 0
+        got = oracle.match(a, b, max_ratio=ratio, max_distance=dist, cross_check=cc)
+        assert np.array_equal(got, oracle.match_numpy(a, b, max_ratio=ratio, max_distance=dist, cross_check=cc))
+        assert np.all(np.diff(got[:, 0].astype(np.int64)) > 0) if len(got) else True
+        if cc and len(got):
+            assert len(set(got[:, 1].tolist())) == len(got)                  # cross-check makes the matching one-to-one
+
+    check()
